@@ -1,0 +1,912 @@
+// The C ABI of include/bof_b200.h: context, argument validation, the device-tile entry points and
+// the host entry points (per-GPU CUDA-stream tile pipelines: host buffer -> H2D -> kernel -> D2H
+// -> host buffer).  The pipelines replace, for this path, the reference's scheduler / cache /
+// io_executor / file_handle stack (src/scheduler/*.cpp, src/file_handles/*.cpp): residency is
+// structural (every output row block is produced by one pass on one GPU), ordering is expressed
+// with CUDA events instead of task parents and overlap checks.
+#include "common.cuh"
+
+#include <algorithm>
+#include <chrono>
+
+using namespace bof;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+bool is_nt(char c) { return c == 'N' || c == 'T'; }
+bool is_rc(char c) { return c == 'R' || c == 'C'; }
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// slots of the context arena
+enum Slot {
+  S_DENSE = 0,     // resident dense operand (B of csrmm, x of csrgemv, Q source of gemm)
+  S_DENSE_T,       // its transposed / split form
+  S_BLK0 = 2,      // per-block buffers, two generations each (b = 0/1 added to the slot id)
+  S_OFFS = 2, S_IDX64 = 4, S_IDX32 = 6, S_VALS = 8, S_CBLK = 10, S_CBLK_T = 12,
+  S_PRAW = 14, S_PPLANES = 16,
+  S_WS = 18,       // kernel workspaces
+  S_OUT0 = 19, S_OUT1, S_OUT2, S_MISC,
+};
+
+cudaEvent_t get_event(bof_ctx* ctx, size_t i) {
+  while (ctx->events.size() <= i) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    ctx->events.push_back(e);
+  }
+  return ctx->events[i];
+}
+
+// pitched host<->device copy; collapses to a flat copy when both sides are tight
+int copy2d(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+           size_t height, cudaMemcpyKind kind, cudaStream_t s) {
+  if (width == 0 || height == 0) return BOF_OK;
+  if (dpitch == width && spitch == width) {
+    BOF_CUDA(ctx, cudaMemcpyAsync(dst, src, width * height, kind, s));
+  } else {
+    BOF_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s));
+  }
+  if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (double)width * height;
+  else if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += (double)width * height;
+  return BOF_OK;
+}
+int copy1d(bof_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  return copy2d(ctx, dst, bytes, src, bytes, bytes, 1, kind, s);
+}
+
+void stats_begin(bof_ctx* ctx) {
+  ctx->stats = bof_stats{};
+  ctx->stats.total_ms = -now_ms();
+  ctx->stats.kernel_launches = -ctx->launches.load();
+}
+void stats_end(bof_ctx* ctx) {
+  ctx->stats.total_ms += now_ms();
+  ctx->stats.kernel_launches += ctx->launches.load();
+}
+
+int sync_all(bof_ctx* ctx) {
+  BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
+  BOF_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+  BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
+  return BOF_OK;
+}
+
+#define BOF_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != BOF_OK) return rc__; \
+  } while (0)
+
+// Canonical form of a GEMM: Cout[Mo x No] (row-major, ldc) = P[Mo x K] * Q[No x K]^T where
+// element (r, kk) of P is psrc[r*p_sr + kk*p_sk] (one of the strides is 1), same for Q.
+struct Canon {
+  int64_t Mo, No, K;
+  const float* psrc; int64_t p_sr, p_sk;
+  const float* qsrc; int64_t q_sr, q_sk;
+  int64_t ldc;
+};
+
+// Leading-dimension defaults and the row/col role table of src/blas/gemm.cpp:52-67.
+int canon_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
+               const float* A, int64_t lda, const float* B, int64_t ldb, int64_t ldc, Canon* out) {
+  BOF_REQUIRE(ctx, is_rc(ord), "gemm: mat_ord must be 'R' or 'C' (got '%c')", ord);
+  BOF_REQUIRE(ctx, is_nt(ta), "gemm: trans_a must be 'N' or 'T' (got '%c')", ta);
+  BOF_REQUIRE(ctx, is_nt(tb), "gemm: trans_b must be 'N' or 'T' (got '%c')", tb);
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
+  const bool col = ord == 'C', tA = ta == 'T', tB = tb == 'T';
+  const int64_t a_cols = (tA != col) ? m : k;  // contiguous extent of A as stored
+  const int64_t b_cols = (tB != col) ? k : n;
+  const int64_t c_cols = col ? m : n;
+  if (lda == 0) lda = a_cols;
+  if (ldb == 0) ldb = b_cols;
+  if (ldc == 0) ldc = c_cols;
+  BOF_REQUIRE(ctx, lda >= a_cols && ldb >= b_cols && ldc >= c_cols, "gemm: leading dimension too small");
+  // op(A)(i, kk) = A[i*a_si + kk*a_sk]: contiguous in kk iff A is stored with k as its inner extent
+  const int64_t a_si = (tA == col) ? lda : 1, a_sk = (tA == col) ? 1 : lda;
+  // op(B)(kk, j) = B[j*b_sj + kk*b_sk]: contiguous in kk iff B is stored with k as its inner extent
+  const int64_t b_sj = (tB != col) ? ldb : 1, b_sk = (tB != col) ? 1 : ldb;
+  Canon c{};
+  c.K = k;
+  c.ldc = ldc;
+  if (!col) {  // C[i*ldc + j]
+    c.Mo = m; c.No = n;
+    c.psrc = A; c.p_sr = a_si; c.p_sk = a_sk;
+    c.qsrc = B; c.q_sr = b_sj; c.q_sk = b_sk;
+  } else {     // column-major C is the row-major transpose: C^T = op(B)^T op(A)^T
+    c.Mo = n; c.No = m;
+    c.psrc = B; c.p_sr = b_sj; c.p_sk = b_sk;
+    c.qsrc = A; c.q_sr = a_si; c.q_sk = a_sk;
+  }
+  *out = c;
+  return BOF_OK;
+}
+
+int64_t padded_k(int64_t k) { return std::max<int64_t>(32, round_up<int64_t>(k, 32)); }
+size_t plane_bytes(int64_t rows, int64_t kp) { return round_up<size_t>((size_t)rows * kp * 4, 256); }
+
+int pick_gemm_path(const bof_ctx* ctx, int64_t Mo, int64_t No, int64_t K) {
+  if (ctx->cfg.gemm_force_path) return ctx->cfg.gemm_force_path;
+  if ((double)Mo * No * K < 2e6) return 3;  // launch-latency territory: CUDA cores, no planes
+  return 2;
+}
+
+int64_t k_chunk_of(const bof_ctx* ctx) {
+  if (ctx->cfg.gemm_k_chunk < 0) return 0;
+  return ctx->cfg.gemm_k_chunk == 0 ? 512 : ctx->cfg.gemm_k_chunk;
+}
+
+// GEMM on device-resident canonical operands with a caller-provided plane workspace.
+int gemm_canon_device(bof_ctx* ctx, cudaStream_t s, const Canon& c, float alpha, float beta, float* C,
+                      void* ws, size_t ws_bytes) {
+  if (c.Mo == 0 || c.No == 0) return BOF_OK;
+  const int path = pick_gemm_path(ctx, c.Mo, c.No, c.K);
+  if (c.K == 0 || path == 3) {
+    // K == 0 degenerates to C = beta*C, which the CUDA-core kernel handles as well
+    return launch_gemm_ffma(ctx, s, c.Mo, c.No, c.K, alpha, c.psrc, c.p_sr, c.p_sk, c.qsrc, c.q_sk, c.q_sr,
+                            beta, C, c.ldc);
+  }
+  const int64_t kp = padded_k(c.K);
+  const size_t pb = plane_bytes(c.Mo, kp), qb = plane_bytes(c.No, kp);
+  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= 2 * pb + 2 * qb + 256, "gemm: workspace too small");
+  uint8_t* base = reinterpret_cast<uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(ws), 256));
+  float* p_hi = reinterpret_cast<float*>(base);
+  float* p_lo = reinterpret_cast<float*>(base + pb);
+  float* q_hi = reinterpret_cast<float*>(base + 2 * pb);
+  float* q_lo = reinterpret_cast<float*>(base + 2 * pb + qb);
+  BOF_TRY(launch_split_planes(ctx, s, c.Mo, c.K, c.psrc, c.p_sr, c.p_sk, p_hi, p_lo, kp));
+  BOF_TRY(launch_split_planes(ctx, s, c.No, c.K, c.qsrc, c.q_sr, c.q_sk, q_hi, q_lo, kp));
+  GemmEpilogue ep;
+  ep.alpha = alpha; ep.beta = beta; ep.C = C; ep.ldc = c.ldc;
+  return launch_gemm_tc(ctx, s, path == 1 ? 1 : 2, c.Mo, c.No, c.K, kp, p_hi, p_lo, q_hi, q_lo, ep, k_chunk_of(ctx));
+}
+
+// Row-block partition by nnz budget (the idea of get_next_blk_size, include/blas_utils.h:72-82):
+// blocks[i] .. blocks[i+1] are the rows of block i.
+std::vector<int64_t> partition_rows(const int64_t* ia, int64_t m, int64_t max_nnz) {
+  std::vector<int64_t> cuts{0};
+  int64_t r = 0;
+  while (r < m) {
+    const int64_t limit = ia[r] + max_nnz;
+    int64_t e = std::upper_bound(ia + r + 1, ia + m + 1, limit) - ia - 1;  // last e with ia[e] <= limit
+    if (e <= r) e = r + 1;  // a single row above the budget still forms a block
+    cuts.push_back(e);
+    r = e;
+  }
+  return cuts;
+}
+
+}  // namespace
+
+namespace bof {
+int slot_reserve(bof_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 256;
+  if (ctx->slot_bytes[slot] < bytes) {
+    if (ctx->slot_ptr[slot]) {
+      // the buffer may still be in use by queued work of a previous call
+      BOF_CUDA(ctx, cudaDeviceSynchronize());
+      BOF_CUDA(ctx, cudaFree(ctx->slot_ptr[slot]));
+      ctx->slot_ptr[slot] = nullptr;
+      ctx->slot_bytes[slot] = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->slot_ptr[slot], bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, BOF_ENOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->slot_bytes[slot] = bytes;
+  }
+  *out = ctx->slot_ptr[slot];
+  return BOF_OK;
+}
+}  // namespace bof
+
+extern "C" {
+
+int bof_abi_version(void) { return 1; }
+
+int bof_ctx_create(const bof_config* cfg, bof_ctx** out) {
+  if (!out) return BOF_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return BOF_ENODEV;
+  }
+  bof_ctx* ctx = new bof_ctx();
+  if (cfg) ctx->cfg = *cfg;
+  ctx->device = ctx->cfg.device;
+  auto bail = [&](int code, const std::string& msg) {
+    g_create_err = msg;
+    delete ctx;
+    return code;
+  };
+  if (ctx->device < 0 || ctx->device >= ndev) return bail(BOF_EINVAL, "device ordinal out of range");
+  if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(BOF_ECUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop{};
+  if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return bail(BOF_ECUDA, cudaGetErrorString(e));
+  if (prop.major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "device %d is sm_%d%d; this library only carries sm_100a code (B200)", ctx->device,
+             prop.major, prop.minor);
+    return bail(BOF_ENODEV, buf);
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  if (ctx->cfg.n_copy_threads <= 0) ctx->cfg.n_copy_threads = 4;
+  if (ctx->cfg.stage_bytes == 0) ctx->cfg.stage_bytes = 64ull << 20;
+  if (ctx->cfg.n_stage_bufs <= 0) ctx->cfg.n_stage_bufs = 4;
+  if (ctx->cfg.csrmm_max_nnz == 0) ctx->cfg.csrmm_max_nnz = 64ull << 20;
+  if (ctx->cfg.gemm_row_block == 0) ctx->cfg.gemm_row_block = 4096;
+  cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking);
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    ctx->tmap_encode = fn;
+  else
+    cudaGetLastError();
+  *out = ctx;
+  return BOF_OK;
+}
+
+int bof_ctx_destroy(bof_ctx* ctx) {
+  if (!ctx) return BOF_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < bof_ctx::kSlots; ++i)
+    if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+  for (auto ev : ctx->events) cudaEventDestroy(ev);
+  if (ctx->compute) cudaStreamDestroy(ctx->compute);
+  if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+  if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+  delete ctx;
+  return BOF_OK;
+}
+
+const char* bof_last_error(const bof_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int bof_get_stats(const bof_ctx* ctx, bof_stats* out) {
+  if (!ctx || !out) return BOF_EINVAL;
+  *out = ctx->stats;
+  return BOF_OK;
+}
+
+int64_t bof_launch_count(const bof_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+// ---- device-tile entry points ---------------------------------------------------------------
+
+size_t bof_spmm_workspace_bytes(char ord, int64_t m, int64_t n, int64_t k) {
+  if (ord != 'C') return 0;
+  return round_up<size_t>((size_t)n * k * 4, 256) + round_up<size_t>((size_t)m * k * 4, 256) + 256;
+}
+
+int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n, int64_t k, float alpha,
+                     const float* vals, const int32_t* idx, const int64_t* offs, const float* B, int64_t ldb,
+                     float beta, float* C, int64_t ldc, void* workspace, size_t workspace_bytes) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, is_rc(ord), "csrmm: ord_b must be 'R' or 'C' (got '%c')", ord);
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && k >= 0, "csrmm: negative dimension");
+  BOF_REQUIRE(ctx, n < (1ll << 31), "csrmm: column count must fit int32 on the device");
+  cudaStream_t s = as_stream(stream);
+  if (m == 0 || k == 0) return BOF_OK;
+  if (ord == 'R') {
+    BOF_REQUIRE(ctx, ldb >= k && ldc >= k, "csrmm: leading dimension too small");
+    return launch_spmm_rm(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+  }
+  // Column-major B (n x k, ldb >= n) and C (m x k, ldc >= m): transpose-on-stage around the
+  // row-major kernel; the gathers need B rows contiguous.
+  BOF_REQUIRE(ctx, ldb >= n && ldc >= m, "csrmm: leading dimension too small");
+  BOF_REQUIRE(ctx, workspace && workspace_bytes >= bof_spmm_workspace_bytes(ord, m, n, k),
+              "csrmm: column-major needs bof_spmm_workspace_bytes() of workspace");
+  uint8_t* base = reinterpret_cast<uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(workspace), 256));
+  float* Bt = reinterpret_cast<float*>(base);
+  float* Ct = reinterpret_cast<float*>(base + round_up<size_t>((size_t)n * k * 4, 256));
+  BOF_TRY(launch_transpose(ctx, s, k, n, B, ldb, Bt, k));
+  BOF_TRY(launch_spmm_rm(ctx, s, m, k, 1.f, vals, idx, offs, Bt, k, 0.f, Ct, k));
+  return launch_transpose_axpby(ctx, s, m, k, alpha, Ct, k, beta, C, ldc);
+}
+
+int bof_spmv_csr_f32(bof_ctx* ctx, void* stream, char trans, int64_t m, int64_t n, const float* vals,
+                     const int32_t* idx, const int64_t* offs, const float* x, float* y) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, is_nt(trans), "csrgemv: trans_a must be 'N' or 'T' (got '%c')", trans);
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && n < (1ll << 31), "csrgemv: bad dimension");
+  return launch_spmv(ctx, as_stream(stream), trans, m, n, vals, idx, offs, x, y);
+}
+
+int bof_idx_narrow(bof_ctx* ctx, void* stream, const int64_t* in, int32_t* out, int64_t count) {
+  if (!ctx) return BOF_EINVAL;
+  return launch_idx_narrow(ctx, as_stream(stream), in, out, count);
+}
+int bof_idx_widen(bof_ctx* ctx, void* stream, const int32_t* in, int64_t* out, int64_t count) {
+  if (!ctx) return BOF_EINVAL;
+  return launch_idx_widen(ctx, as_stream(stream), in, out, count);
+}
+
+size_t bof_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  const int64_t kp = padded_k(k);
+  return 2 * plane_bytes(m, kp) + 2 * plane_bytes(n, kp) + 512;
+}
+
+int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
+                  float alpha, const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
+                  int64_t ldc, void* workspace, size_t workspace_bytes) {
+  if (!ctx) return BOF_EINVAL;
+  Canon c;
+  BOF_TRY(canon_gemm(ctx, ord, ta, tb, m, n, k, A, lda, B, ldb, ldc, &c));
+  return gemm_canon_device(ctx, as_stream(stream), c, alpha, beta, C, workspace, workspace_bytes);
+}
+
+size_t bof_csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz) { return csr2csc_workspace_bytes(m, n, nnz); }
+
+int bof_csr2csc(bof_ctx* ctx, void* stream, int64_t m, int64_t n, int64_t nnz, const int64_t* offs,
+                const int32_t* idx, const float* vals, int64_t* offs_t, int32_t* idx_t, float* vals_t,
+                void* workspace, size_t workspace_bytes) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && nnz >= 0, "csrcsc: negative dimension");
+  return launch_csr2csc(ctx, as_stream(stream), m, n, nnz, offs, idx, vals, offs_t, idx_t, vals_t, workspace,
+                        workspace_bytes);
+}
+
+int bof_row_sqnorm_f32(bof_ctx* ctx, void* stream, int64_t rows, int64_t dim, const float* X, int64_t ldx,
+                       float* out) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, rows >= 0 && dim >= 0 && ldx >= dim, "row_sqnorm: bad dimension");
+  return launch_row_sqnorm(ctx, as_stream(stream), rows, dim, X, ldx, out);
+}
+
+size_t bof_kmeans_point_planes_bytes(int64_t npoints, int64_t dim) { return 2 * plane_bytes(npoints, padded_k(dim)) + 256; }
+
+size_t bof_kmeans_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim, int with_point_planes) {
+  size_t b = 2 * plane_bytes(ncenters, padded_k(dim)) + 512;
+  if (with_point_planes) b += bof_kmeans_point_planes_bytes(npoints, dim);
+  return b;
+}
+
+int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64_t dim, const float* points,
+                              void* points_planes) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, npoints >= 0 && dim > 0 && points_planes, "kmeans: bad argument");
+  const int64_t kp = padded_k(dim);
+  uint8_t* base = reinterpret_cast<uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(points_planes), 256));
+  return launch_split_planes(ctx, as_stream(stream), npoints, dim, points, dim, 1, reinterpret_cast<float*>(base),
+                             reinterpret_cast<float*>(base + plane_bytes(npoints, kp)), kp);
+}
+
+int bof_kmeans_assign(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+                      const float* points, const float* centers, const float* c_l2sq, const float* p_l2sq,
+                      int32_t* assign, const void* points_planes, void* workspace, size_t workspace_bytes) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, npoints >= 0 && ncenters > 0 && dim > 0, "kmeans: bad dimension");
+  BOF_REQUIRE(ctx, workspace && workspace_bytes >= bof_kmeans_workspace_bytes(npoints, ncenters, dim, points_planes == nullptr),
+              "kmeans: workspace too small");
+  if (npoints == 0) return BOF_OK;
+  cudaStream_t s = as_stream(stream);
+  const int64_t kp = padded_k(dim);
+  uint8_t* base = reinterpret_cast<uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(workspace), 256));
+  float* c_hi = reinterpret_cast<float*>(base);
+  float* c_lo = reinterpret_cast<float*>(base + plane_bytes(ncenters, kp));
+  BOF_TRY(launch_split_planes(ctx, s, ncenters, dim, centers, dim, 1, c_hi, c_lo, kp));
+  const uint8_t* pp;
+  if (points_planes) {
+    pp = reinterpret_cast<const uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(points_planes), 256));
+  } else {
+    uint8_t* mine = base + 2 * plane_bytes(ncenters, kp);
+    BOF_TRY(bof_kmeans_prepare_points(ctx, stream, npoints, dim, points, mine));
+    pp = reinterpret_cast<const uint8_t*>(round_up<uintptr_t>(reinterpret_cast<uintptr_t>(mine), 256));
+  }
+  GemmEpilogue ep;
+  ep.C = nullptr;
+  ep.row_add = p_l2sq;
+  ep.col_add = c_l2sq;
+  ep.argmin_out = assign;
+  const int cg = ctx->cfg.gemm_force_path == 1 ? 1 : 2;
+  return launch_gemm_tc(ctx, s, cg, npoints, ncenters, dim, kp, reinterpret_cast<const float*>(pp),
+                        reinterpret_cast<const float*>(pp + plane_bytes(npoints, kp)), c_hi, c_lo, ep, 0);
+}
+
+size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters) {
+  return kmeans_reduce_workspace_bytes(npoints, ncenters);
+}
+
+int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+                      const float* points, const int32_t* assign, float* sums, float* counts, void* workspace,
+                      size_t workspace_bytes) {
+  if (!ctx) return BOF_EINVAL;
+  return launch_kmeans_reduce_ws(ctx, as_stream(stream), npoints, ncenters, dim, points, assign, sums, counts,
+                                 workspace, workspace_bytes);
+}
+
+int bof_kmeans_finalize(bof_ctx* ctx, void* stream, int64_t ncenters, int64_t dim, const float* sums,
+                        const float* counts, float* centers, float* c_l2sq) {
+  if (!ctx) return BOF_EINVAL;
+  return launch_kmeans_finalize(ctx, as_stream(stream), ncenters, dim, sums, counts, centers, c_l2sq);
+}
+
+// ---- host entry points -------------------------------------------------------------------------
+
+// flash::csrmm.  'N': B is uploaded once and stays resident; A streams in nnz-balanced row blocks
+// (offsets, indices, values), double-buffered: while block i runs, block i+1 uploads and block
+// i-1's C rows download.  'T': whole-matrix csr2csc on the device, then the same kernel.
+int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
+                   const float* a, const int64_t* ia, const int64_t* ja, char ord_b, const float* b, float* c) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, is_nt(trans_a), "csrmm: unrecognized value for param trans_a = '%c'", trans_a);
+  BOF_REQUIRE(ctx, is_rc(ord_b), "csrmm: unrecognized value for param ord_b = '%c'", ord_b);
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && k >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrmm: bad dimension");
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  stats_begin(ctx);
+  const int64_t out_rows = trans_a == 'N' ? m : n;   // rows of C
+  const int64_t in_rows = trans_a == 'N' ? n : m;    // rows of B
+  if (out_rows == 0 || k == 0) { stats_end(ctx); return BOF_OK; }
+  const bool colmaj = ord_b == 'C';
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+
+  // resident dense operand, always row-major [in_rows x k] on the device
+  float* Bd = nullptr;
+  BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)in_rows * k, &Bd));
+  if (colmaj) {
+    float* Braw = nullptr;
+    BOF_TRY(slot_reserve(ctx, S_DENSE_T, (size_t)in_rows * k, &Braw));
+    BOF_TRY(copy1d(ctx, Braw, b, (size_t)in_rows * k * 4, H2D, ctx->h2d));
+    cudaEvent_t evB = get_event(ctx, 0);
+    BOF_CUDA(ctx, cudaEventRecord(evB, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
+    BOF_TRY(launch_transpose(ctx, ctx->compute, k, in_rows, Braw, in_rows, Bd, k));
+  } else {
+    BOF_TRY(copy1d(ctx, Bd, b, (size_t)in_rows * k * 4, H2D, ctx->h2d));
+    cudaEvent_t evB = get_event(ctx, 0);
+    BOF_CUDA(ctx, cudaEventRecord(evB, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
+  }
+
+  const int64_t* offs_host = ia;
+  const int64_t nnz = ia[m] - ia[0];
+  std::vector<int64_t> tr_offs_host;  // only for 'T'
+  const int32_t* idx_dev_all = nullptr;  // 'T': transposed matrix resident on the device
+  const float* vals_dev_all = nullptr;
+  const int64_t* offs_dev_all = nullptr;
+
+  if (trans_a == 'T') {
+    // A^T in CSR on the device (K6), then the no-transpose kernel on n rows.
+    BOF_REQUIRE(ctx, nnz < (1ll << 31), "csrmm('T'): nnz must be below 2^31");
+    int64_t *offs_d, *offs_t, *idx64;
+    int32_t *idx32, *idx_t;
+    float *vals_d, *vals_t;
+    void* ws;
+    const size_t wsb = csr2csc_workspace_bytes(m, n, nnz);
+    BOF_TRY(slot_reserve(ctx, S_OFFS, (size_t)m + 1, &offs_d));
+    BOF_TRY(slot_reserve(ctx, S_IDX64, (size_t)std::max<int64_t>(nnz, 1), &idx64));
+    BOF_TRY(slot_reserve(ctx, S_IDX32, (size_t)std::max<int64_t>(nnz, 1), &idx32));
+    BOF_TRY(slot_reserve(ctx, S_VALS, (size_t)std::max<int64_t>(nnz, 1), &vals_d));
+    BOF_TRY(slot_reserve(ctx, S_OUT0, (size_t)n + 1, &offs_t));
+    BOF_TRY(slot_reserve(ctx, S_OUT1, (size_t)std::max<int64_t>(nnz, 1), &idx_t));
+    BOF_TRY(slot_reserve(ctx, S_OUT2, (size_t)std::max<int64_t>(nnz, 1), &vals_t));
+    BOF_TRY(slot_reserve(ctx, S_WS, wsb, &ws));
+    BOF_TRY(copy1d(ctx, offs_d, ia, (size_t)(m + 1) * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, idx64, ja, (size_t)nnz * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, vals_d, a, (size_t)nnz * 4, H2D, ctx->h2d));
+    cudaEvent_t ev = get_event(ctx, 1);
+    BOF_CUDA(ctx, cudaEventRecord(ev, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev, 0));
+    BOF_TRY(launch_idx_narrow(ctx, ctx->compute, idx64, idx32, nnz));
+    BOF_TRY(launch_csr2csc(ctx, ctx->compute, m, n, nnz, offs_d, idx32, vals_d, offs_t, idx_t, vals_t, ws, wsb));
+    offs_dev_all = offs_t;
+    idx_dev_all = idx_t;
+    vals_dev_all = vals_t;
+  }
+
+  if (trans_a == 'T') {
+    // whole C on the device (n x k); beta needs the old C
+    float* Cd = nullptr;
+    BOF_TRY(slot_reserve(ctx, S_CBLK, (size_t)out_rows * k, &Cd));
+    float* Cio = Cd;  // what is copied from/to the host
+    float* Ccm = nullptr;
+    if (colmaj) { BOF_TRY(slot_reserve(ctx, S_CBLK_T, (size_t)out_rows * k, &Ccm)); Cio = Ccm; }
+    if (beta != 0.f) {
+      BOF_TRY(copy1d(ctx, Cio, c, (size_t)out_rows * k * 4, H2D, ctx->h2d));
+      cudaEvent_t ev = get_event(ctx, 2);
+      BOF_CUDA(ctx, cudaEventRecord(ev, ctx->h2d));
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev, 0));
+    }
+    if (colmaj) {
+      BOF_TRY(launch_spmm_rm(ctx, ctx->compute, out_rows, k, 1.f, vals_dev_all, idx_dev_all, offs_dev_all, Bd, k, 0.f, Cd, k));
+      BOF_TRY(launch_transpose_axpby(ctx, ctx->compute, out_rows, k, alpha, Cd, k, beta, Ccm, out_rows));
+    } else {
+      BOF_TRY(launch_spmm_rm(ctx, ctx->compute, out_rows, k, alpha, vals_dev_all, idx_dev_all, offs_dev_all, Bd, k, beta, Cd, k));
+    }
+    BOF_TRY(copy1d(ctx, c, Cio, (size_t)out_rows * k * 4, D2H, ctx->compute));
+    BOF_TRY(sync_all(ctx));
+    stats_end(ctx);
+    return BOF_OK;
+  }
+
+  // ---- 'N': streamed row blocks ----
+  int64_t budget = (int64_t)ctx->cfg.csrmm_max_nnz;
+  budget = std::min(budget, std::max<int64_t>(nnz / 8, 1 << 20));  // >= 8 blocks when the matrix is big enough
+  const std::vector<int64_t> cuts = partition_rows(offs_host, m, budget);
+  const int nblk = (int)cuts.size() - 1;
+  int64_t max_rows = 1, max_nnz = 1;
+  for (int i = 0; i < nblk; ++i) {
+    max_rows = std::max(max_rows, cuts[i + 1] - cuts[i]);
+    max_nnz = std::max(max_nnz, offs_host[cuts[i + 1]] - offs_host[cuts[i]]);
+  }
+  int64_t* offs_d[2]; int64_t* idx64_d[2]; int32_t* idx32_d[2]; float* vals_d[2]; float* cblk[2]; float* cblk_t[2] = {nullptr, nullptr};
+  for (int g = 0; g < 2; ++g) {
+    BOF_TRY(slot_reserve(ctx, S_OFFS + g, (size_t)max_rows + 1, &offs_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_IDX64 + g, (size_t)max_nnz, &idx64_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_IDX32 + g, (size_t)max_nnz, &idx32_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_VALS + g, (size_t)max_nnz, &vals_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)max_rows * k, &cblk[g]));
+    if (colmaj) BOF_TRY(slot_reserve(ctx, S_CBLK_T + g, (size_t)max_rows * k, &cblk_t[g]));
+  }
+  // events: 4+g uploaded, 6+g computed, 8+g downloaded
+  bool used[2] = {false, false};
+  for (int i = 0; i < nblk; ++i) {
+    const int g = i & 1;
+    const int64_t r0 = cuts[i], r1 = cuts[i + 1], rows = r1 - r0;
+    const int64_t z0 = offs_host[r0] - offs_host[0], z1 = offs_host[r1] - offs_host[0], bnnz = z1 - z0;
+    cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
+    if (used[g]) {
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_done, 0));   // inputs of block i-2 consumed
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_down, 0));   // its C rows left the device
+    }
+    BOF_TRY(copy1d(ctx, offs_d[g], offs_host + r0, (size_t)(rows + 1) * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, idx64_d[g], ja + z0, (size_t)bnnz * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, vals_d[g], a + z0, (size_t)bnnz * 4, H2D, ctx->h2d));
+    float* c_io = colmaj ? cblk_t[g] : cblk[g];
+    if (beta != 0.f) {
+      if (colmaj) BOF_TRY(copy2d(ctx, c_io, (size_t)rows * 4, c + r0, (size_t)m * 4, (size_t)rows * 4, (size_t)k, H2D, ctx->h2d));
+      else BOF_TRY(copy1d(ctx, c_io, c + r0 * k, (size_t)rows * k * 4, H2D, ctx->h2d));
+    }
+    BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_up, 0));
+    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_down, 0));
+    BOF_TRY(launch_idx_narrow(ctx, ctx->compute, idx64_d[g], idx32_d[g], bnnz));
+    if (colmaj) {
+      BOF_TRY(launch_spmm_rm(ctx, ctx->compute, rows, k, 1.f, vals_d[g], idx32_d[g], offs_d[g], Bd, k, 0.f, cblk[g], k));
+      BOF_TRY(launch_transpose_axpby(ctx, ctx->compute, rows, k, alpha, cblk[g], k, beta, cblk_t[g], rows));
+    } else {
+      BOF_TRY(launch_spmm_rm(ctx, ctx->compute, rows, k, alpha, vals_d[g], idx32_d[g], offs_d[g], Bd, k, beta, cblk[g], k));
+    }
+    BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ev_done, 0));
+    if (colmaj) BOF_TRY(copy2d(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, D2H, ctx->d2h));
+    else BOF_TRY(copy1d(ctx, c + r0 * k, c_io, (size_t)rows * k * 4, D2H, ctx->d2h));
+    BOF_CUDA(ctx, cudaEventRecord(ev_down, ctx->d2h));
+    used[g] = true;
+  }
+  BOF_TRY(sync_all(ctx));
+  stats_end(ctx);
+  return BOF_OK;
+}
+
+// flash::gemm.  The canonical Q operand (op(B)^T for row-major problems) is uploaded and split
+// into TF32 planes once; the canonical P operand and the output stream in row blocks,
+// double-buffered (upload / split + MMA / download overlap).  The reference's k-dimension
+// accumulate chain (src/blas/gemm.cpp:114-126) is an I/O artefact: the whole k extent is reduced
+// on the device, so each C block crosses PCIe once.
+int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
+                  float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc) {
+  if (!ctx) return BOF_EINVAL;
+  Canon cn;
+  BOF_TRY(canon_gemm(ctx, ord, ta, tb, m, n, k, a, lda, b, ldb, ldc, &cn));
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  stats_begin(ctx);
+  if (cn.Mo == 0 || cn.No == 0) { stats_end(ctx); return BOF_OK; }
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  const int path = pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
+  const int64_t K = cn.K, kp = padded_k(K);
+  const bool tensor = (K > 0 && path != 3);
+
+  // upload a canonical operand block rows [r0, r1) as a tight device matrix; returns its strides
+  auto upload_rows = [&](const float* src, int64_t s_r, int64_t s_k, int64_t r0, int64_t r1, float* dst,
+                         int64_t* d_sr, int64_t* d_sk, cudaStream_t s) -> int {
+    const int64_t rows = r1 - r0;
+    if (K == 0) { *d_sr = 1; *d_sk = 1; return BOF_OK; }
+    if (s_k == 1) {  // rows contiguous in k
+      *d_sr = K; *d_sk = 1;
+      return copy2d(ctx, dst, (size_t)K * 4, src + r0 * s_r, (size_t)s_r * 4, (size_t)K * 4, (size_t)rows, H2D, s);
+    }
+    *d_sr = 1; *d_sk = rows;  // stored k-major: a column range of a [K x ld] matrix
+    return copy2d(ctx, dst, (size_t)rows * 4, src + r0, (size_t)s_k * 4, (size_t)rows * 4, (size_t)K, H2D, s);
+  };
+
+  // Q: resident
+  float* qraw = nullptr;
+  float* qplanes = nullptr;
+  int64_t q_sr = 1, q_sk = 1;
+  BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)cn.No * std::max<int64_t>(K, 1), &qraw));
+  BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, 0, cn.No, qraw, &q_sr, &q_sk, ctx->h2d));
+  cudaEvent_t evQ = get_event(ctx, 0);
+  BOF_CUDA(ctx, cudaEventRecord(evQ, ctx->h2d));
+  BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evQ, 0));
+  const size_t qb = plane_bytes(cn.No, kp);
+  if (tensor) {
+    void* p;
+    BOF_TRY(slot_reserve(ctx, S_DENSE_T, 2 * qb, &p));
+    qplanes = static_cast<float*>(p);
+    BOF_TRY(launch_split_planes(ctx, ctx->compute, cn.No, K, qraw, q_sr, q_sk, qplanes,
+                                reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(qplanes) + qb), kp));
+  }
+
+  int64_t rb = (int64_t)ctx->cfg.gemm_row_block;
+  rb = std::max<int64_t>(256, round_up<int64_t>(rb, 256));
+  rb = std::min(rb, round_up<int64_t>(cn.Mo, 256));
+  const int nblk = (int)ceil_div<int64_t>(cn.Mo, rb);
+  const size_t pb = plane_bytes(rb, kp);
+  float* praw[2]; float* pplanes[2] = {nullptr, nullptr}; float* cblk[2];
+  for (int g = 0; g < 2; ++g) {
+    BOF_TRY(slot_reserve(ctx, S_PRAW + g, (size_t)rb * std::max<int64_t>(K, 1), &praw[g]));
+    if (tensor) { void* p; BOF_TRY(slot_reserve(ctx, S_PPLANES + g, 2 * pb, &p)); pplanes[g] = static_cast<float*>(p); }
+    BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)rb * cn.No, &cblk[g]));
+  }
+  bool used[2] = {false, false};
+  for (int i = 0; i < nblk; ++i) {
+    const int g = i & 1;
+    const int64_t r0 = (int64_t)i * rb, r1 = std::min(cn.Mo, r0 + rb), rows = r1 - r0;
+    cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_split = get_event(ctx, 6 + g), ev_done = get_event(ctx, 8 + g),
+                ev_down = get_event(ctx, 10 + g);
+    if (used[g]) {
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, tensor ? ev_split : ev_done, 0));  // raw P of block i-2 consumed
+      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_down, 0));     // C block buffer free
+    }
+    int64_t p_sr, p_sk;
+    BOF_TRY(upload_rows(cn.psrc, cn.p_sr, cn.p_sk, r0, r1, praw[g], &p_sr, &p_sk, ctx->h2d));
+    if (beta != 0.f)
+      BOF_TRY(copy2d(ctx, cblk[g], (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
+    BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_up, 0));
+    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_down, 0));
+    if (tensor) {
+      float* p_hi = pplanes[g];
+      float* p_lo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pplanes[g]) + pb);
+      BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi, p_lo, kp));
+      BOF_CUDA(ctx, cudaEventRecord(ev_split, ctx->compute));
+      GemmEpilogue ep;
+      ep.alpha = alpha; ep.beta = beta; ep.C = cblk[g]; ep.ldc = cn.No;
+      BOF_TRY(launch_gemm_tc(ctx, ctx->compute, path == 1 ? 1 : 2, rows, cn.No, K, kp, p_hi, p_lo, qplanes,
+                             reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(qplanes) + qb), ep, k_chunk_of(ctx)));
+    } else {
+      BOF_TRY(launch_gemm_ffma(ctx, ctx->compute, rows, cn.No, K, alpha, praw[g], p_sr, p_sk, qraw, q_sk, q_sr, beta,
+                               cblk[g], cn.No));
+    }
+    BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ev_done, 0));
+    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk[g], (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
+    BOF_CUDA(ctx, cudaEventRecord(ev_down, ctx->d2h));
+    used[g] = true;
+  }
+  BOF_TRY(sync_all(ctx));
+  stats_end(ctx);
+  return BOF_OK;
+}
+
+// flash::csrgemv: x resident, A streams in row blocks; 'N' writes disjoint y rows, 'T' accumulates
+// every block into the full y on the device (zeroed once, as src/blas/csrgemv.cpp:64 does).
+int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a, const int64_t* ia,
+                     const int64_t* ja, const float* b, float* c) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, is_nt(trans_a), "csrgemv trans_a error : expected=N or T, found=%c", trans_a);
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrgemv: bad dimension");
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  stats_begin(ctx);
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  const bool tr = trans_a == 'T';
+  const int64_t xlen = tr ? m : n, ylen = tr ? n : m;
+  if (ylen == 0) { stats_end(ctx); return BOF_OK; }
+  float *xd, *yd;
+  BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)std::max<int64_t>(xlen, 1), &xd));
+  BOF_TRY(slot_reserve(ctx, S_CBLK, (size_t)ylen, &yd));
+  BOF_TRY(copy1d(ctx, xd, b, (size_t)xlen * 4, H2D, ctx->h2d));
+  cudaEvent_t evx = get_event(ctx, 0);
+  BOF_CUDA(ctx, cudaEventRecord(evx, ctx->h2d));
+  BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evx, 0));
+  BOF_CUDA(ctx, cudaMemsetAsync(yd, 0, (size_t)ylen * 4, ctx->compute));
+
+  const int64_t nnz = ia[m] - ia[0];
+  int64_t budget = std::min<int64_t>((int64_t)ctx->cfg.csrmm_max_nnz, std::max<int64_t>(nnz / 8, 1 << 20));
+  const std::vector<int64_t> cuts = partition_rows(ia, m, budget);
+  const int nblk = (int)cuts.size() - 1;
+  int64_t max_rows = 1, max_nnz = 1;
+  for (int i = 0; i < nblk; ++i) {
+    max_rows = std::max(max_rows, cuts[i + 1] - cuts[i]);
+    max_nnz = std::max(max_nnz, ia[cuts[i + 1]] - ia[cuts[i]]);
+  }
+  int64_t* offs_d[2]; int64_t* idx64_d[2]; int32_t* idx32_d[2]; float* vals_d[2];
+  for (int g = 0; g < 2; ++g) {
+    BOF_TRY(slot_reserve(ctx, S_OFFS + g, (size_t)max_rows + 1, &offs_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_IDX64 + g, (size_t)max_nnz, &idx64_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_IDX32 + g, (size_t)max_nnz, &idx32_d[g]));
+    BOF_TRY(slot_reserve(ctx, S_VALS + g, (size_t)max_nnz, &vals_d[g]));
+  }
+  bool used[2] = {false, false};
+  for (int i = 0; i < nblk; ++i) {
+    const int g = i & 1;
+    const int64_t r0 = cuts[i], r1 = cuts[i + 1], rows = r1 - r0;
+    const int64_t z0 = ia[r0] - ia[0], bnnz = ia[r1] - ia[r0];
+    cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_done = get_event(ctx, 6 + g);
+    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_done, 0));
+    BOF_TRY(copy1d(ctx, offs_d[g], ia + r0, (size_t)(rows + 1) * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, idx64_d[g], ja + z0, (size_t)bnnz * 8, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, vals_d[g], a + z0, (size_t)bnnz * 4, H2D, ctx->h2d));
+    BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_up, 0));
+    BOF_TRY(launch_idx_narrow(ctx, ctx->compute, idx64_d[g], idx32_d[g], bnnz));
+    if (!tr) {
+      BOF_TRY(launch_spmv(ctx, ctx->compute, 'N', rows, n, vals_d[g], idx32_d[g], offs_d[g], xd, yd + r0));
+    } else {
+      // y += A_blk^T x_blk : launch the accumulate kernel directly (y was zeroed once above)
+      BOF_TRY(launch_spmv(ctx, ctx->compute, 't', rows, n, vals_d[g], idx32_d[g], offs_d[g], xd + r0, yd));
+    }
+    BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
+    used[g] = true;
+  }
+  BOF_TRY(copy1d(ctx, c, yd, (size_t)ylen * 4, D2H, ctx->compute));
+  BOF_TRY(sync_all(ctx));
+  stats_end(ctx);
+  return BOF_OK;
+}
+
+// flash::csrcsc: the whole matrix is transposed in HBM in one shot (the reference's two-phase
+// row-block transpose + column-block merge exists only because a block had to fit in DRAM).
+int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const int64_t* ja, const float* a,
+                    int64_t* ia_tr, int64_t* ja_tr, float* a_tr) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_REQUIRE(ctx, m >= 0 && n >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrcsc: bad dimension");
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  stats_begin(ctx);
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  const int64_t nnz = ia[m] - ia[0];
+  BOF_REQUIRE(ctx, nnz >= 0 && nnz < (1ll << 31), "csrcsc: nnz must be in [0, 2^31)");
+  const size_t z = (size_t)std::max<int64_t>(nnz, 1);
+  int64_t *offs_d, *offs_t, *idx64;
+  int32_t *idx32, *idx_t;
+  float *vals_d, *vals_t;
+  void* ws;
+  const size_t wsb = csr2csc_workspace_bytes(m, n, nnz);
+  BOF_TRY(slot_reserve(ctx, S_OFFS, (size_t)m + 1, &offs_d));
+  BOF_TRY(slot_reserve(ctx, S_IDX64, z, &idx64));
+  BOF_TRY(slot_reserve(ctx, S_IDX32, z, &idx32));
+  BOF_TRY(slot_reserve(ctx, S_VALS, z, &vals_d));
+  BOF_TRY(slot_reserve(ctx, S_OUT0, (size_t)n + 1, &offs_t));
+  BOF_TRY(slot_reserve(ctx, S_OUT1, z, &idx_t));
+  BOF_TRY(slot_reserve(ctx, S_OUT2, z, &vals_t));
+  BOF_TRY(slot_reserve(ctx, S_WS, wsb, &ws));
+  // values ride a second stream so that both copy engines' queues stay busy
+  BOF_TRY(copy1d(ctx, offs_d, ia, (size_t)(m + 1) * 8, H2D, ctx->h2d));
+  BOF_TRY(copy1d(ctx, idx64, ja, (size_t)nnz * 8, H2D, ctx->h2d));
+  BOF_TRY(copy1d(ctx, vals_d, a, (size_t)nnz * 4, H2D, ctx->h2d));
+  cudaEvent_t ev = get_event(ctx, 0);
+  BOF_CUDA(ctx, cudaEventRecord(ev, ctx->h2d));
+  BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev, 0));
+  BOF_TRY(launch_idx_narrow(ctx, ctx->compute, idx64, idx32, nnz));
+  BOF_TRY(launch_csr2csc(ctx, ctx->compute, m, n, nnz, offs_d, idx32, vals_d, offs_t, idx_t, vals_t, ws, wsb));
+  // the int64 staging buffer of the input indices is free again: reuse it for the widened output
+  BOF_TRY(launch_idx_widen(ctx, ctx->compute, idx_t, idx64, nnz));
+  cudaEvent_t evk = get_event(ctx, 1);
+  BOF_CUDA(ctx, cudaEventRecord(evk, ctx->compute));
+  BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, evk, 0));
+  BOF_TRY(copy1d(ctx, a_tr, vals_t, (size_t)nnz * 4, D2H, ctx->d2h));
+  BOF_TRY(copy1d(ctx, ja_tr, idx64, (size_t)nnz * 8, D2H, ctx->compute));
+  BOF_TRY(copy1d(ctx, ia_tr, offs_t, (size_t)(n + 1) * 8, D2H, ctx->compute));  // offsets last, as csrcsc.cpp:150
+  BOF_TRY(sync_all(ctx));
+  stats_end(ctx);
+  return BOF_OK;
+}
+
+// ---- k-means: points shard resident across iterations -------------------------------------------
+
+struct bof_kmeans {
+  bof_ctx* ctx;
+  int64_t npoints, ncenters, dim;
+  float* points;        // P x dim
+  void* point_planes;   // TF32 hi/lo planes of the points (filled once)
+  float* p_l2sq;        // P
+  float* centers;       // K x dim
+  float* c_l2sq;        // K
+  float* partial;       // [K*dim sums | K counts]
+  int32_t* assign;      // P
+  void* ws_assign; size_t ws_assign_bytes;
+  void* ws_reduce; size_t ws_reduce_bytes;
+  int64_t* assign64;    // P, for bof_kmeans_get
+};
+
+static void kmeans_free(bof_kmeans* km) {
+  if (!km) return;
+  void* ptrs[] = {km->points, km->point_planes, km->p_l2sq, km->centers, km->c_l2sq, km->partial,
+                  km->assign, km->ws_assign, km->ws_reduce, km->assign64};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete km;
+}
+
+int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim, const float* points_host,
+                    const float* centers_host, bof_kmeans** out) {
+  if (!ctx || !out) return BOF_EINVAL;
+  *out = nullptr;
+  BOF_REQUIRE(ctx, npoints >= 0 && ncenters > 0 && dim > 0 && npoints < (1ll << 31), "kmeans: bad dimension");
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  bof_kmeans* km = new bof_kmeans();
+  km->ctx = ctx; km->npoints = npoints; km->ncenters = ncenters; km->dim = dim;
+  const size_t P = (size_t)std::max<int64_t>(npoints, 1);
+  km->ws_assign_bytes = bof_kmeans_workspace_bytes(npoints, ncenters, dim, 0);
+  km->ws_reduce_bytes = kmeans_reduce_workspace_bytes(npoints, ncenters);
+  struct Req { void** p; size_t bytes; } reqs[] = {
+      {(void**)&km->points, P * dim * 4}, {&km->point_planes, bof_kmeans_point_planes_bytes(npoints, dim)},
+      {(void**)&km->p_l2sq, P * 4}, {(void**)&km->centers, (size_t)ncenters * dim * 4},
+      {(void**)&km->c_l2sq, (size_t)ncenters * 4}, {(void**)&km->partial, ((size_t)ncenters * dim + ncenters) * 4},
+      {(void**)&km->assign, P * 4}, {&km->ws_assign, km->ws_assign_bytes}, {&km->ws_reduce, km->ws_reduce_bytes},
+      {(void**)&km->assign64, P * 8}};
+  for (auto& r : reqs) {
+    if (cudaMalloc(r.p, r.bytes) != cudaSuccess) {
+      cudaGetLastError();
+      kmeans_free(km);
+      return fail(ctx, BOF_ENOMEM, "kmeans: cudaMalloc of %zu bytes failed", r.bytes);
+    }
+  }
+  cudaStream_t s = ctx->compute;
+  auto guard = [&](int rc) { if (rc != BOF_OK) kmeans_free(km); return rc; };
+  if (int rc = guard(copy1d(ctx, km->points, points_host, (size_t)npoints * dim * 4, cudaMemcpyHostToDevice, s))) return rc;
+  if (int rc = guard(copy1d(ctx, km->centers, centers_host, (size_t)ncenters * dim * 4, cudaMemcpyHostToDevice, s))) return rc;
+  if (int rc = guard(launch_row_sqnorm(ctx, s, npoints, dim, km->points, dim, km->p_l2sq))) return rc;
+  if (int rc = guard(launch_row_sqnorm(ctx, s, ncenters, dim, km->centers, dim, km->c_l2sq))) return rc;
+  if (int rc = guard(bof_kmeans_prepare_points(ctx, s, npoints, dim, km->points, km->point_planes))) return rc;
+  if (cudaStreamSynchronize(s) != cudaSuccess) { kmeans_free(km); return fail(ctx, BOF_ECUDA, "kmeans: upload failed"); }
+  *out = km;
+  return BOF_OK;
+}
+
+int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_floats) {
+  if (!km) return BOF_EINVAL;
+  bof_ctx* ctx = km->ctx;
+  cudaStream_t s = ctx->compute;
+  BOF_TRY(bof_kmeans_assign(ctx, s, km->npoints, km->ncenters, km->dim, km->points, km->centers, km->c_l2sq,
+                            km->p_l2sq, km->assign, km->point_planes, km->ws_assign, km->ws_assign_bytes));
+  BOF_TRY(launch_kmeans_reduce_ws(ctx, s, km->npoints, km->ncenters, km->dim, km->points, km->assign, km->partial,
+                                  km->partial + km->ncenters * km->dim, km->ws_reduce, km->ws_reduce_bytes));
+  if (dev_partial) *dev_partial = km->partial;
+  if (partial_floats) *partial_floats = (size_t)km->ncenters * km->dim + km->ncenters;
+  return BOF_OK;
+}
+
+int bof_kmeans_update(bof_kmeans* km) {
+  if (!km) return BOF_EINVAL;
+  return launch_kmeans_finalize(km->ctx, km->ctx->compute, km->ncenters, km->dim, km->partial,
+                                km->partial + km->ncenters * km->dim, km->centers, km->c_l2sq);
+}
+
+int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host) {
+  if (!km) return BOF_EINVAL;
+  bof_ctx* ctx = km->ctx;
+  cudaStream_t s = ctx->compute;
+  if (centers_host) BOF_TRY(copy1d(ctx, centers_host, km->centers, (size_t)km->ncenters * km->dim * 4, cudaMemcpyDeviceToHost, s));
+  if (assign_host && km->npoints > 0) {
+    BOF_TRY(launch_idx_widen(ctx, s, km->assign, km->assign64, km->npoints));
+    BOF_TRY(copy1d(ctx, assign_host, km->assign64, (size_t)km->npoints * 8, cudaMemcpyDeviceToHost, s));
+  }
+  BOF_CUDA(ctx, cudaStreamSynchronize(s));
+  return BOF_OK;
+}
+
+void* bof_kmeans_stream(bof_kmeans* km) { return km ? (void*)km->ctx->compute : nullptr; }
+
+int bof_kmeans_close(bof_kmeans* km) {
+  if (!km) return BOF_OK;
+  cudaStreamSynchronize(km->ctx->compute);
+  kmeans_free(km);
+  return BOF_OK;
+}
+
+}  // extern "C"

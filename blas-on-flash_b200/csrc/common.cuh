@@ -1,0 +1,169 @@
+// Shared plumbing for the sm_100a kernels and the C ABI (include/bof_b200.h).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bof_b200.h"
+
+namespace bof {
+
+constexpr int kNumSmsFallback = 148;
+
+struct PinnedBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace bof
+
+// The opaque context of the C ABI: one per process/GPU (replaces the static flash::sched,
+// src/lib_funcs.cpp:9 of the reference).
+struct bof_ctx {
+  bof_config cfg{};
+  int device = 0;
+  int num_sms = bof::kNumSmsFallback;
+  size_t l2_bytes = 0;
+  cudaStream_t compute = nullptr;  // kernels of the host entry points
+  cudaStream_t h2d = nullptr;      // uploads
+  cudaStream_t d2h = nullptr;      // downloads
+  std::vector<bof::PinnedBuf> stage_in, stage_out;
+  std::string err;
+  bof_stats stats{};
+  std::atomic<int64_t> launches{0};
+  void* tmap_encode = nullptr;  // cuTensorMapEncodeTiled, fetched at ctx creation
+  // Grow-only device buffers owned by the context and reused across host entry points, so that
+  // steady-state calls do no cudaMalloc (the reference's counterpart is the Program Cache budget,
+  // src/scheduler/cache.cpp).
+  static constexpr int kSlots = 24;
+  void* slot_ptr[kSlots] = {};
+  size_t slot_bytes[kSlots] = {};
+  std::vector<cudaEvent_t> events;
+};
+
+namespace bof {
+
+inline int fail(bof_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  if (getenv("BOF_VERBOSE")) fprintf(stderr, "[bof_b200] error %d: %s\n", code, buf);
+  return code;
+}
+
+#define BOF_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return bof::fail((ctx), BOF_ECUDA, "%s failed: %s (%s:%d)", #expr,                     \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+  } while (0)
+
+#define BOF_LAUNCH_CHECK(ctx, what)                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess)                                                                  \
+      return bof::fail((ctx), BOF_ECUDA, "launch of %s failed: %s (%s:%d)", (what),          \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                                 \
+  } while (0)
+
+#define BOF_REQUIRE(ctx, cond, ...)                                                          \
+  do {                                                                                       \
+    if (!(cond)) return bof::fail((ctx), BOF_EINVAL, __VA_ARGS__);                           \
+  } while (0)
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+template <typename T>
+__host__ __device__ constexpr T round_up(T a, T b) {
+  return ceil_div(a, b) * b;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Device buffer `slot` of at least `bytes` (contents are not preserved when it has to grow).
+int slot_reserve(bof_ctx* ctx, int slot, size_t bytes, void** out);
+template <typename T>
+int slot_reserve(bof_ctx* ctx, int slot, size_t count, T** out) {
+  void* p = nullptr;
+  int rc = slot_reserve(ctx, slot, count * sizeof(T), &p);
+  *out = static_cast<T*>(p);
+  return rc;
+}
+
+// ---- kernel launchers implemented in the .cu files (device pointers, no validation) --------
+
+int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
+                   const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
+                   int64_t ldb, float beta, float* C, int64_t ldc);
+int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
+                const int32_t* idx, const int64_t* offs, const float* x, float* y);
+int launch_idx_narrow(bof_ctx* ctx, cudaStream_t s, const int64_t* in, int32_t* out, int64_t n);
+int launch_idx_widen(bof_ctx* ctx, cudaStream_t s, const int32_t* in, int64_t* out, int64_t n);
+// out[c * ldo + r] = in[r * ldi + c] for an rows x cols row-major input
+int launch_transpose(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, const float* in,
+                     int64_t ldi, float* out, int64_t ldo);
+// out = alpha * in^T + beta * out, same indexing as launch_transpose (beta==0: out not read)
+int launch_transpose_axpby(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, float alpha,
+                           const float* in, int64_t ldi, float beta, float* out, int64_t ldo);
+
+// TF32 split of a logical R x K operand whose element (r, kk) lives at src[r*s_r + kk*s_k]
+// (exactly one of s_r, s_k is 1) into K-major planes hi/lo of row stride kp (multiple of 32).
+int launch_split_planes(bof_ctx* ctx, cudaStream_t s, int64_t R, int64_t K, const float* src,
+                        int64_t s_r, int64_t s_k, float* hi, float* lo, int64_t kp);
+
+struct GemmEpilogue {
+  // plain GEMM: Cout[i * ldc + j] = alpha * acc + beta * Cout
+  float alpha = 1.f, beta = 0.f;
+  float* C = nullptr;
+  int64_t ldc = 0;
+  // k-means assign epilogue (C == nullptr): per row running argmin over j of
+  // |fl(fl(-2*acc + col_add[j]) + row_add[i])|
+  const float* row_add = nullptr;
+  const float* col_add = nullptr;
+  int32_t* argmin_out = nullptr;
+};
+
+// Tensor-core core: acc[i, j] = sum_k P[i, k] * Q[j, k] with P = (p_hi, p_lo) M x kp planes and
+// Q = (q_hi, q_lo) N x kp planes, 3xTF32 (lo*hi + hi*lo + hi*hi), fp32 accumulate in TMEM with an
+// fp32 round-to-nearest fold every k_chunk elements of k.
+int launch_gemm_tc(bof_ctx* ctx, cudaStream_t s, int cta_group, int64_t M, int64_t N, int64_t K,
+                   int64_t kp, const float* p_hi, const float* p_lo, const float* q_hi,
+                   const float* q_lo, const GemmEpilogue& ep, int64_t k_chunk);
+
+// CUDA-core fp32 GEMM for ragged / unaligned shapes: C[i*ldc+j] = alpha*sum_k A(i,k)*B(k,j) +
+// beta*C with A(i,k) = A[i*a_r + k*a_k], B(k,j) = B[k*b_k + j*b_c].
+int launch_gemm_ffma(bof_ctx* ctx, cudaStream_t s, int64_t M, int64_t N, int64_t K, float alpha,
+                     const float* A, int64_t a_r, int64_t a_k, const float* B, int64_t b_k,
+                     int64_t b_c, float beta, float* C, int64_t ldc);
+
+int launch_row_sqnorm(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t dim, const float* X,
+                      int64_t ldx, float* out);
+size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters);
+int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
+                            int64_t dim, const float* points, const int32_t* assign, float* sums,
+                            float* counts, void* ws, size_t ws_bytes);
+int launch_kmeans_finalize(bof_ctx* ctx, cudaStream_t s, int64_t ncenters, int64_t dim,
+                           const float* sums, const float* counts, float* centers, float* c_l2sq);
+
+size_t csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz);
+int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t nnz,
+                   const int64_t* offs, const int32_t* idx, const float* vals, int64_t* offs_t,
+                   int32_t* idx_t, float* vals_t, void* ws, size_t ws_bytes);
+
+}  // namespace bof

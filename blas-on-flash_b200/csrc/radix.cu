@@ -1,0 +1,520 @@
+// K6/K7 (stable CSR -> CSC) and K10/K11 (k-means centroid reduce, row norms) for sm_100a.
+//
+// Reference bodies replaced:
+//   mkl_scsrcsc + index rebase      include/tasks/csrcsc_task.h:68-80
+//   row-block-ordered segment merge include/tasks/csrcsc_task.h:143-162
+//   bucket + cblas_saxpy loop       drivers/in_mem_kmeans.cpp:105-125
+//   cblas_sdot row norms            drivers/in_mem_kmeans.cpp:75-78,179-182
+//
+// The transpose is the unique *stable* counting sort of the nonzeros by column.  It is built from
+// least-significant-digit radix passes (8-bit digits), each pass = per-tile digit histogram ->
+// device-wide exclusive scan -> ranked scatter.  Ranks come from warp match/ballot on warp-private
+// counters, so there is no atomic anywhere and the result is bit-reproducible: within a column the
+// entries keep ascending source row, duplicates keep storage order -- exactly what mkl_scsrcsc on
+// row blocks followed by the reference's in-order merge produces.
+//
+// All of it is HBM-bound byte shuffling; tiles are staged through shared memory so that the
+// scattered runs leave the SM as contiguous segments.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace bof {
+namespace {
+
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_IPT = 16;                       // items per thread
+constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 8192 items per tile
+constexpr int RS_BINS = 256;
+constexpr int RS_CNT_STRIDE = RS_BINS + 1;       // +1: sentinel bin for out-of-range items
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// counts[digit * num_tiles + tile] = number of keys of the tile whose digit is `digit`
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
+                  uint32_t* __restrict__ counts, unsigned num_tiles) {
+  __shared__ uint32_t cnt[RS_WARPS][RS_CNT_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * RS_CNT_STRIDE; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t warp_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * 32 * RS_IPT;
+#pragma unroll 4
+  for (int r = 0; r < RS_IPT; ++r) {
+    const int64_t i = warp_base + r * 32 + lane;
+    const uint32_t d = (i < n) ? ((__ldcs(keys + i) >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if ((peers & lanemask_lt()) == 0) cnt[warp][d] += __popc(peers);  // one writer per digit
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < RS_BINS) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) t += cnt[w][threadIdx.x];
+    counts[(size_t)threadIdx.x * num_tiles + blockIdx.x] = t;
+  }
+}
+
+struct ScatterSmem {
+  uint32_t stage[RS_TILE];
+  uint16_t sdig[RS_TILE];
+  uint32_t cnt[RS_WARPS][RS_CNT_STRIDE];
+  uint32_t digit_off[RS_BINS + 1];   // start of each digit inside the block-sorted tile
+  uint32_t gbase[RS_BINS];           // global start of (digit, this tile)
+};
+
+// Stable scatter of one tile.  offsets = exclusive scan of the histogram kernel's counts.
+// Moves the key and up to two 32-bit payloads.
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                     const uint32_t* __restrict__ p1_in, uint32_t* __restrict__ p1_out,
+                     const uint32_t* __restrict__ p2_in, uint32_t* __restrict__ p2_out, int64_t n,
+                     int shift, const uint32_t* __restrict__ offsets, unsigned num_tiles) {
+  extern __shared__ uint8_t rs_smem_raw[];
+  ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(rs_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * RS_CNT_STRIDE; i += RS_THREADS) (&sm.cnt[0][0])[i] = 0;
+  if (threadIdx.x < RS_BINS) sm.gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * num_tiles + blockIdx.x];
+  __syncthreads();
+
+  const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t warp_base = tile_base + (int64_t)warp * 32 * RS_IPT;
+  const int tile_count = (int)min((int64_t)RS_TILE, n - tile_base);
+
+  uint32_t key[RS_IPT];
+  uint16_t rank[RS_IPT];
+  uint16_t dig[RS_IPT];
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const int64_t i = warp_base + r * 32 + lane;
+    key[r] = (i < n) ? __ldcs(keys_in + i) : 0u;
+    const uint32_t d = (i < n) ? ((key[r] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t old = sm.cnt[warp][d];
+    __syncwarp();
+    if ((peers & lanemask_lt()) == 0) sm.cnt[warp][d] = old + __popc(peers);
+    __syncwarp();
+    rank[r] = (uint16_t)(old + __popc(peers & lanemask_lt()));
+    dig[r] = (uint16_t)d;
+  }
+  __syncthreads();
+
+  // per digit: exclusive prefix over warps (in place), digit totals -> exclusive scan over digits
+  uint32_t total = 0;
+  if (threadIdx.x < RS_BINS) {
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t t = sm.cnt[w][threadIdx.x];
+      sm.cnt[w][threadIdx.x] = total;
+      total += t;
+    }
+  }
+  // block-wide exclusive scan of `total` over the first 256 threads (8 warps)
+  {
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __shared__ uint32_t warp_tot[RS_WARPS];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t add = 0;
+    for (int w = 0; w < warp; ++w) add += warp_tot[w];
+    if (threadIdx.x < RS_BINS) sm.digit_off[threadIdx.x] = add + incl - total;
+    if (threadIdx.x == RS_BINS - 1) sm.digit_off[RS_BINS] = add + incl;
+  }
+  __syncthreads();
+
+  uint16_t pos[RS_IPT];
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const uint32_t d = dig[r];
+    pos[r] = (d < 256u) ? (uint16_t)(sm.digit_off[d] + sm.cnt[warp][d] + rank[r]) : (uint16_t)0xffff;
+  }
+
+  // keys: local sort into smem, then contiguous runs to global
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r)
+    if (pos[r] != 0xffff) {
+      sm.stage[pos[r]] = key[r];
+      sm.sdig[pos[r]] = dig[r];
+    }
+  __syncthreads();
+  for (int s = threadIdx.x; s < tile_count; s += RS_THREADS) {
+    const uint32_t d = sm.sdig[s];
+    keys_out[(size_t)sm.gbase[d] + (s - sm.digit_off[d])] = sm.stage[s];
+  }
+  // payloads reuse the staging buffer
+  const uint32_t* pin[2] = {p1_in, p2_in};
+  uint32_t* pout[2] = {p1_out, p2_out};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (pin[q] == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+      const int64_t i = warp_base + r * 32 + lane;
+      if (pos[r] != 0xffff) sm.stage[pos[r]] = __ldcs(pin[q] + i);
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < tile_count; s += RS_THREADS) {
+      const uint32_t d = sm.sdig[s];
+      pout[q][(size_t)sm.gbase[d] + (s - sm.digit_off[d])] = sm.stage[s];
+    }
+  }
+}
+
+// ---- device-wide exclusive scan of uint32 (in place), three kernels ---------------------------
+constexpr int SC_THREADS = 512;
+constexpr int SC_IPT = 8;
+constexpr int SC_CHUNK = SC_THREADS * SC_IPT;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total_out) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t add = 0, tot = 0;
+  for (int w = 0; w < SC_THREADS / 32; ++w) {
+    const uint32_t t = wsum[w];
+    if (w < warp) add += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total_out = tot;
+  return add + incl - v;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+scan_reduce_kernel(const uint32_t* __restrict__ data, int64_t n, uint32_t* __restrict__ block_sums) {
+  const int64_t base = (int64_t)blockIdx.x * SC_CHUNK;
+  uint32_t s = 0;
+#pragma unroll
+  for (int u = 0; u < SC_IPT; ++u) {
+    const int64_t i = base + u * SC_THREADS + threadIdx.x;
+    if (i < n) s += data[i];
+  }
+  uint32_t tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+scan_blocksums_kernel(uint32_t* __restrict__ block_sums, int64_t nb) {
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < nb; base += SC_THREADS) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = (i < nb) ? block_sums[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(v, &tot);
+    if (i < nb) block_sums[i] = carry + ex;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+scan_apply_kernel(uint32_t* __restrict__ data, int64_t n, const uint32_t* __restrict__ block_sums) {
+  // thread t owns SC_IPT consecutive elements so that the scan order is the index order
+  const int64_t base = (int64_t)blockIdx.x * SC_CHUNK + (int64_t)threadIdx.x * SC_IPT;
+  uint32_t v[SC_IPT];
+  uint32_t s = 0;
+#pragma unroll
+  for (int u = 0; u < SC_IPT; ++u) {
+    v[u] = (base + u < n) ? data[base + u] : 0u;
+    s += v[u];
+  }
+  uint32_t tot;
+  uint32_t run = block_excl_scan(s, &tot) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int u = 0; u < SC_IPT; ++u) {
+    if (base + u < n) data[base + u] = run;
+    run += v[u];
+  }
+}
+
+// rows[j] = source row of nonzero j (a warp per row)
+__global__ void __launch_bounds__(256)
+expand_rows_kernel(int64_t m, const int64_t* __restrict__ offs, uint32_t* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const int64_t base = offs[0];
+  const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+  for (int64_t j = beg + lane; j < end; j += 32) rows[j] = (uint32_t)row;
+}
+
+// seg_offs[c] = first position whose (sorted) key is >= c, for c in [0, nseg]; int64 or fp32 out
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+segment_offsets_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, int64_t nseg,
+                       OutT* __restrict__ seg_offs) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+    const int64_t lo = (i == 0) ? 0 : (int64_t)sorted_keys[i - 1] + 1;
+    const int64_t hi = (i == n) ? nseg : (int64_t)sorted_keys[i];
+    for (int64_t c = lo; c <= hi; ++c) seg_offs[c] = (OutT)i;
+  }
+}
+
+__global__ void iota_kernel(uint32_t* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)i;
+}
+
+int key_bits(int64_t nkeys) {
+  int b = 1;
+  while (b < 32 && ((int64_t)1 << b) < nkeys) ++b;
+  return b;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t counts_bytes(int64_t n) {
+  const int64_t tiles = ceil_div<int64_t>(std::max<int64_t>(n, 1), RS_TILE);
+  const int64_t ncounts = tiles * RS_BINS;
+  const int64_t nblocks = ceil_div<int64_t>(ncounts, SC_CHUNK);
+  return align_up((size_t)ncounts * 4) + align_up((size_t)nblocks * 4);
+}
+
+int exclusive_scan_u32(bof_ctx* ctx, cudaStream_t s, uint32_t* data, int64_t n, uint32_t* block_sums) {
+  const int64_t nb = ceil_div<int64_t>(n, SC_CHUNK);
+  scan_reduce_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(data, n, block_sums);
+  BOF_LAUNCH_CHECK(ctx, "scan_reduce_kernel");
+  scan_blocksums_kernel<<<1, SC_THREADS, 0, s>>>(block_sums, nb);
+  BOF_LAUNCH_CHECK(ctx, "scan_blocksums_kernel");
+  scan_apply_kernel<<<(unsigned)nb, SC_THREADS, 0, s>>>(data, n, block_sums);
+  BOF_LAUNCH_CHECK(ctx, "scan_apply_kernel");
+  return BOF_OK;
+}
+
+struct Triple {
+  uint32_t* key;
+  uint32_t* p1;
+  uint32_t* p2;
+};
+
+// One stable pass on digit `shift`: (in) -> (out).  `counts` holds tiles*256 + scan block sums.
+int radix_pass(bof_ctx* ctx, cudaStream_t s, int64_t n, int shift, const uint32_t* key_in,
+               const uint32_t* p1_in, const uint32_t* p2_in, Triple out, uint32_t* counts) {
+  const int64_t tiles = ceil_div<int64_t>(n, RS_TILE);
+  const int64_t ncounts = tiles * RS_BINS;
+  uint32_t* block_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(counts) + align_up((size_t)ncounts * 4));
+  static bool attr_set = false;
+  if (!attr_set) {
+    BOF_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ScatterSmem)));
+    attr_set = true;
+  }
+  radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(key_in, n, shift, counts, (unsigned)tiles);
+  BOF_LAUNCH_CHECK(ctx, "radix_hist_kernel");
+  int rc = exclusive_scan_u32(ctx, s, counts, ncounts, block_sums);
+  if (rc) return rc;
+  radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, sizeof(ScatterSmem), s>>>(
+      key_in, out.key, p1_in, out.p1, p2_in, out.p2, n, shift, counts, (unsigned)tiles);
+  BOF_LAUNCH_CHECK(ctx, "radix_scatter_kernel");
+  return BOF_OK;
+}
+
+// ---- k-means ------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+row_sqnorm_kernel(int64_t rows, int64_t dim, const float* __restrict__ X, int64_t ldx,
+                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* x = X + row * ldx;
+  float acc = 0.f;
+  for (int64_t j = lane; j < dim; j += 32) {
+    const float v = __ldg(x + j);
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
+// One block per cluster: sums[c, j] = sum of x_p[j] over the cluster's points in ascending p
+// (sequential fp32 adds: deterministic, same order as the reference's saxpy loop).
+__global__ void __launch_bounds__(256)
+kmeans_segment_sum_kernel(int64_t dim, const float* __restrict__ points,
+                          const uint32_t* __restrict__ sorted_ids, const float* __restrict__ seg_offs_f,
+                          const int64_t* __restrict__ seg_offs, float* __restrict__ sums,
+                          float* __restrict__ counts) {
+  (void)seg_offs_f;
+  const int64_t c = blockIdx.x;
+  const int64_t beg = seg_offs[c], end = seg_offs[c + 1];
+  for (int64_t j0 = 0; j0 < dim; j0 += blockDim.x) {
+    const int64_t j = j0 + threadIdx.x;
+    float acc = 0.f;
+    if (j < dim) {
+      int64_t i = beg;
+      for (; i + 8 <= end; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(points + (int64_t)sorted_ids[i + u] * dim + j);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; i < end; ++i) acc += __ldcs(points + (int64_t)sorted_ids[i] * dim + j);
+      sums[c * dim + j] = acc;
+    }
+  }
+  if (threadIdx.x == 0) counts[c] = (float)(end - beg);
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_finalize_kernel(int64_t dim, const float* __restrict__ sums, const float* __restrict__ counts,
+                       float* __restrict__ centers, float* __restrict__ c_l2sq) {
+  __shared__ float red[8];
+  const int64_t c = blockIdx.x;
+  const float cnt = counts[c];
+  const float inv = cnt > 0.f ? 1.f / cnt : 0.f;
+  float acc = 0.f;
+  for (int64_t j = threadIdx.x; j < dim; j += blockDim.x) {
+    const float v = cnt > 0.f ? sums[c * dim + j] * inv : 0.f;  // empty cluster => zero vector
+    centers[c * dim + j] = v;
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    c_l2sq[c] = t;
+  }
+}
+
+}  // namespace
+
+size_t csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz) {
+  (void)m;
+  (void)n;
+  const size_t arr = align_up((size_t)std::max<int64_t>(nnz, 1) * 4);
+  return 7 * arr + counts_bytes(nnz) + 256;
+}
+
+int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t nnz,
+                   const int64_t* offs, const int32_t* idx, const float* vals, int64_t* offs_t,
+                   int32_t* idx_t, float* vals_t, void* ws, size_t ws_bytes) {
+  BOF_REQUIRE(ctx, nnz >= 0 && nnz < (1ll << 31), "csr2csc: nnz must be below 2^31");
+  BOF_REQUIRE(ctx, m < (1ll << 31) && n < (1ll << 31), "csr2csc: dimensions must be below 2^31");
+  if (nnz == 0) {
+    BOF_CUDA(ctx, cudaMemsetAsync(offs_t, 0, (size_t)(n + 1) * sizeof(int64_t), s));
+    return BOF_OK;
+  }
+  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= csr2csc_workspace_bytes(m, n, nnz), "csr2csc: workspace too small");
+  const size_t arr = align_up((size_t)nnz * 4);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  uint32_t* rows0 = reinterpret_cast<uint32_t*>(base);
+  Triple X{reinterpret_cast<uint32_t*>(base + arr), reinterpret_cast<uint32_t*>(base + 2 * arr),
+           reinterpret_cast<uint32_t*>(base + 3 * arr)};
+  Triple Y{reinterpret_cast<uint32_t*>(base + 4 * arr), reinterpret_cast<uint32_t*>(base + 5 * arr),
+           reinterpret_cast<uint32_t*>(base + 6 * arr)};
+  uint32_t* counts = reinterpret_cast<uint32_t*>(base + 7 * arr);
+
+  expand_rows_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, s>>>(m, offs, rows0);
+  BOF_LAUNCH_CHECK(ctx, "expand_rows_kernel");
+
+  const int passes = ceil_div(key_bits(n), 8);
+  const uint32_t* kin = reinterpret_cast<const uint32_t*>(idx);
+  const uint32_t* rin = rows0;
+  const uint32_t* vin = reinterpret_cast<const uint32_t*>(vals);
+  uint32_t* final_keys = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    Triple dst = (p % 2 == 0) ? X : Y;
+    if (p == passes - 1) {
+      // last pass lands in the caller's arrays; the sorted keys go to the idle key buffer
+      final_keys = dst.key;
+      dst.p1 = reinterpret_cast<uint32_t*>(idx_t);
+      dst.p2 = reinterpret_cast<uint32_t*>(vals_t);
+    }
+    int rc = radix_pass(ctx, s, nnz, 8 * p, kin, rin, vin, dst, counts);
+    if (rc) return rc;
+    kin = dst.key;
+    rin = dst.p1;
+    vin = dst.p2;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 256), (int64_t)ctx->num_sms * 32);
+  segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(final_keys, nnz, n, offs_t);
+  BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
+  return BOF_OK;
+}
+
+int launch_row_sqnorm(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t dim, const float* X,
+                      int64_t ldx, float* out) {
+  if (rows == 0) return BOF_OK;
+  row_sqnorm_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, s>>>(rows, dim, X, ldx, out);
+  BOF_LAUNCH_CHECK(ctx, "row_sqnorm_kernel");
+  return BOF_OK;
+}
+
+size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters) {
+  const size_t arr = align_up((size_t)std::max<int64_t>(npoints, 1) * 4);
+  return 4 * arr + counts_bytes(npoints) + align_up((size_t)(ncenters + 1) * 8) + 256;
+}
+
+int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
+                            int64_t dim, const float* points, const int32_t* assign, float* sums,
+                            float* counts_out, void* ws, size_t ws_bytes) {
+  BOF_REQUIRE(ctx, npoints < (1ll << 31) && ncenters < (1ll << 31), "kmeans_reduce: extents must be below 2^31");
+  BOF_REQUIRE(ctx, ncenters > 0 && dim > 0, "kmeans_reduce: empty problem");
+  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= kmeans_reduce_workspace_bytes(npoints, ncenters),
+              "kmeans_reduce: workspace too small");
+  const size_t arr = align_up((size_t)std::max<int64_t>(npoints, 1) * 4);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  Triple X{reinterpret_cast<uint32_t*>(base), reinterpret_cast<uint32_t*>(base + arr), nullptr};
+  Triple Y{reinterpret_cast<uint32_t*>(base + 2 * arr), reinterpret_cast<uint32_t*>(base + 3 * arr), nullptr};
+  uint32_t* counts = reinterpret_cast<uint32_t*>(base + 4 * arr);
+  int64_t* seg = reinterpret_cast<int64_t*>(base + 4 * arr + counts_bytes(npoints));
+
+  const uint32_t* kin = reinterpret_cast<const uint32_t*>(assign);
+  const uint32_t* pin = nullptr;
+  if (npoints > 0) {
+    // ids 0..P-1 as the payload of the first pass
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(npoints, 256), (int64_t)ctx->num_sms * 32);
+    iota_kernel<<<grid, 256, 0, s>>>(Y.p1, npoints);
+    BOF_LAUNCH_CHECK(ctx, "iota_kernel");
+    pin = Y.p1;
+    const int passes = ceil_div(key_bits(ncenters), 8);
+    for (int p = 0; p < passes; ++p) {
+      Triple dst = (p % 2 == 0) ? X : Y;
+      int rc = radix_pass(ctx, s, npoints, 8 * p, kin, pin, nullptr, dst, counts);
+      if (rc) return rc;
+      kin = dst.key;
+      pin = dst.p1;
+    }
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(npoints + 1, 256), (int64_t)ctx->num_sms * 32);
+  segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(kin, npoints, ncenters, seg);
+  BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
+  kmeans_segment_sum_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, points, pin, nullptr, seg, sums, counts_out);
+  BOF_LAUNCH_CHECK(ctx, "kmeans_segment_sum_kernel");
+  return BOF_OK;
+}
+
+int launch_kmeans_finalize(bof_ctx* ctx, cudaStream_t s, int64_t ncenters, int64_t dim,
+                           const float* sums, const float* counts, float* centers, float* c_l2sq) {
+  if (ncenters == 0) return BOF_OK;
+  kmeans_finalize_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, sums, counts, centers, c_l2sq);
+  BOF_LAUNCH_CHECK(ctx, "kmeans_finalize_kernel");
+  return BOF_OK;
+}
+
+}  // namespace bof

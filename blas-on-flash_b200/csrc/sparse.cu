@@ -1,0 +1,341 @@
+// K1/K2/K4/K5: CSR x dense (SpMM) and CSR x vector (SpMV) for sm_100a, plus the small
+// index/transposition helpers the staging path needs.
+//
+// Reference bodies replaced:
+//   mkl_scsrmm            include/tasks/csrmm_task.h:219-228 (row-major), :290-312 (col-major)
+//   mkl_cspblas_scsrgemv  include/tasks/csrgemv_task.h:60-83 ('N'), :152-179 ('T')
+//
+// Both are HBM/L2-bound gathers: one group of L lanes owns one output row; the (col, val) stream
+// of the row is read coalesced with a streaming hint (it is touched exactly once) and each
+// nonzero pulls one k-wide row of B as float4 per lane through the read-only path, several rows
+// in flight per group so that the gather latency is covered.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace bof {
+
+namespace {
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void fma4(float4& acc, float v, const float4& b) {
+  acc.x = fmaf(v, b.x, acc.x);
+  acc.y = fmaf(v, b.y, acc.y);
+  acc.z = fmaf(v, b.z, acc.z);
+  acc.w = fmaf(v, b.w, acc.w);
+}
+
+// L lanes per row, KV float4 per lane: one pass covers 4*L*KV columns starting at
+// blockIdx.y * 4*L*KV.  Requires B, C 16-byte aligned, ldb/ldc multiples of 4; the column
+// tail (k not a multiple of 4*L) is masked per float4, k itself must be a multiple of 4.
+template <int L, int KV>
+__global__ void __launch_bounds__(256)
+spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
+                       const int32_t* __restrict__ idx, const int64_t* __restrict__ offs,
+                       const float* __restrict__ B, int64_t ldb, float beta, float* __restrict__ C,
+                       int64_t ldc) {
+  constexpr int ROWS_PER_WARP = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L;       // which row of the warp
+  const int sl = lane % L;        // lane within the row group
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row = warp_global * ROWS_PER_WARP + sub;
+  const int64_t col0 = (int64_t)blockIdx.y * (4 * L * KV) + 4 * sl;
+  const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
+  const bool row_ok = row < m;
+
+  const int64_t base = offs[0];
+  int64_t beg = 0, end = 0;
+  if (row_ok) {
+    beg = offs[row] - base;
+    end = offs[row + 1] - base;
+  }
+
+  bool col_ok[KV];
+  float4 acc[KV];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    col_ok[v] = (col0 + (int64_t)v * 4 * L) < k;
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  for (int64_t j = beg; j < end; j += L) {
+    const int64_t mine = j + sl;
+    int32_t c = 0;
+    float a = 0.f;
+    if (mine < end) {
+      c = __ldcs(idx + mine);
+      a = __ldcs(vals + mine);
+    }
+    const int cnt = (int)min((int64_t)L, end - j);
+    // a == 0 for the padded lanes, so the full-width loop below is safe: it gathers row
+    // idx 0 of B at most L-1 extra times on the last chunk; keep it exact instead:
+    int t = 0;
+    for (; t + 4 <= cnt; t += 4) {
+      int32_t cc[4];
+      float aa[4];
+      float4 bb[4][KV];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cc[u] = __shfl_sync(gmask, c, t + u, L);
+        aa[u] = __shfl_sync(gmask, a, t + u, L);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* brow = B + (int64_t)cc[u] * ldb + col0;
+#pragma unroll
+        for (int v = 0; v < KV; ++v)
+          bb[u][v] = col_ok[v] ? ldg_f4(brow + v * 4 * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < KV; ++v) fma4(acc[v], aa[u], bb[u][v]);
+    }
+    for (; t < cnt; ++t) {
+      const int32_t cc = __shfl_sync(gmask, c, t, L);
+      const float aa = __shfl_sync(gmask, a, t, L);
+      const float* brow = B + (int64_t)cc * ldb + col0;
+#pragma unroll
+      for (int v = 0; v < KV; ++v)
+        if (col_ok[v]) fma4(acc[v], aa, ldg_f4(brow + v * 4 * L));
+    }
+  }
+
+  if (!row_ok) return;
+  float* crow = C + row * ldc + col0;
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    if (!col_ok[v]) continue;
+    float4 r;
+    r.x = alpha * acc[v].x;
+    r.y = alpha * acc[v].y;
+    r.z = alpha * acc[v].z;
+    r.w = alpha * acc[v].w;
+    float4* dst = reinterpret_cast<float4*>(crow + v * 4 * L);
+    if (beta != 0.f) {
+      const float4 old = *dst;
+      r.x = fmaf(beta, old.x, r.x);
+      r.y = fmaf(beta, old.y, r.y);
+      r.z = fmaf(beta, old.z, r.z);
+      r.w = fmaf(beta, old.w, r.w);
+    }
+    __stcs(dst, r);
+  }
+}
+
+// Any k, any alignment: a warp owns a row and strides over the columns.
+__global__ void __launch_bounds__(256)
+spmm_csr_rm_generic_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
+                           const int32_t* __restrict__ idx, const int64_t* __restrict__ offs,
+                           const float* __restrict__ B, int64_t ldb, float beta,
+                           float* __restrict__ C, int64_t ldc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const int64_t base = offs[0];
+  const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+  for (int64_t c0 = 0; c0 < k; c0 += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t j = beg; j < end; ++j) {
+      const float a = __ldg(vals + j);
+      const float* brow = B + (int64_t)__ldg(idx + j) * ldb + c0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t cc = lane + 32 * u;
+        if (c0 + cc < k) acc[u] = fmaf(a, __ldg(brow + cc), acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t cc = c0 + lane + 32 * u;
+      if (cc < k) {
+        float r = alpha * acc[u];
+        if (beta != 0.f) r = fmaf(beta, C[row * ldc + cc], r);
+        C[row * ldc + cc] = r;
+      }
+    }
+  }
+}
+
+// y = A x : L lanes per row, shuffle reduction inside the group.
+template <int L>
+__global__ void __launch_bounds__(256)
+spmv_csr_n_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                  const int64_t* __restrict__ offs, const float* __restrict__ x,
+                  float* __restrict__ y) {
+  constexpr int ROWS_PER_WARP = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L;
+  const int64_t row =
+      ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS_PER_WARP + sub;
+  const int64_t base = offs[0];
+  int64_t beg = 0, end = 0;
+  if (row < m) {
+    beg = offs[row] - base;
+    end = offs[row + 1] - base;
+  }
+  float acc = 0.f;
+  for (int64_t j = beg + sl; j < end; j += L) acc = fmaf(__ldcs(vals + j), __ldg(x + __ldcs(idx + j)), acc);
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, L);
+  if (row < m && sl == 0) y[row] = acc;
+}
+
+// y += A^T x : every nonzero (r, c, v) contributes v * x[r] to y[c]; red.global.add.f32
+// replaces the reference's mutex-serialised vector add (csrgemv_task.h:170-176).
+template <int L>
+__global__ void __launch_bounds__(256)
+spmv_csr_t_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                  const int64_t* __restrict__ offs, const float* __restrict__ x,
+                  float* __restrict__ y) {
+  constexpr int ROWS_PER_WARP = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L;
+  const int64_t row =
+      ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS_PER_WARP + sub;
+  if (row >= m) return;
+  const int64_t base = offs[0];
+  const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+  const float xr = __ldg(x + row);
+  for (int64_t j = beg + sl; j < end; j += L) atomicAdd(y + __ldcs(idx + j), __ldcs(vals + j) * xr);
+}
+
+__global__ void idx_narrow_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out,
+                                  int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (int32_t)__ldcs(in + i);
+}
+__global__ void idx_widen_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out,
+                                 int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (int64_t)__ldcs(in + i);
+}
+
+// out[c*ldo + r] = alpha * in[r*ldi + c] + beta * out[c*ldo + r]; 32x32 smem tiles, +1 padding.
+template <bool AXPBY>
+__global__ void __launch_bounds__(256)
+transpose_kernel(int64_t rows, int64_t cols, float alpha, const float* __restrict__ in,
+                 int64_t ldi, float beta, float* __restrict__ out, int64_t ldo,
+                 unsigned tiles_c) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  // linear tile index: either extent may exceed the 65535 limit of grid.y
+  const int64_t r0 = (int64_t)(blockIdx.x / tiles_c) * 32, c0 = (int64_t)(blockIdx.x % tiles_c) * 32;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[r * ldi + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) {
+      float v = tile[tx][i];
+      if (AXPBY) {
+        v *= alpha;
+        if (beta != 0.f) v = fmaf(beta, out[c * ldo + r], v);
+      }
+      out[c * ldo + r] = v;
+    }
+  }
+}
+
+template <int L, int KV>
+int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
+                    const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
+                    int64_t ldb, float beta, float* C, int64_t ldc) {
+  constexpr int ROWS_PER_BLOCK = 8 * (32 / L);
+  dim3 grid((unsigned)ceil_div<int64_t>(m, ROWS_PER_BLOCK),
+            (unsigned)ceil_div<int64_t>(k, 4 * L * KV));
+  spmm_csr_rm_vec_kernel<L, KV><<<grid, 256, 0, s>>>(m, k, alpha, vals, idx, offs, B, ldb, beta,
+                                                     C, ldc);
+  BOF_LAUNCH_CHECK(ctx, "spmm_csr_rm_vec_kernel");
+  return BOF_OK;
+}
+
+}  // namespace
+
+int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
+                   const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
+                   int64_t ldb, float beta, float* C, int64_t ldc) {
+  if (m == 0 || k == 0) return BOF_OK;
+  const bool vec_ok =
+      (k % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && aligned16(B) && aligned16(C);
+  if (!vec_ok) {
+    spmm_csr_rm_generic_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, s>>>(
+        m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+    BOF_LAUNCH_CHECK(ctx, "spmm_csr_rm_generic_kernel");
+    return BOF_OK;
+  }
+#define BOF_SPMM(L, KV) \
+  return spmm_vec_launch<L, KV>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
+  if (k <= 16) BOF_SPMM(4, 1);
+  if (k <= 32) BOF_SPMM(8, 1);
+  if (k <= 64) BOF_SPMM(16, 1);
+  if (k <= 128) BOF_SPMM(32, 1);
+  BOF_SPMM(32, 2);
+#undef BOF_SPMM
+}
+
+int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
+                const int32_t* idx, const int64_t* offs, const float* x, float* y) {
+  // 'T' zeroes y first (src/blas/csrgemv.cpp:64); 't' accumulates into y as it is, which is
+  // what a row-block pipeline needs for every block after the memset.
+  if (trans == 'T' || trans == 't') {
+    if (trans == 'T') BOF_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s));
+    if (m == 0) return BOF_OK;
+    spmv_csr_t_kernel<16><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
+    BOF_LAUNCH_CHECK(ctx, "spmv_csr_t_kernel");
+    return BOF_OK;
+  }
+  if (m == 0) return BOF_OK;
+  spmv_csr_n_kernel<16><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
+  BOF_LAUNCH_CHECK(ctx, "spmv_csr_n_kernel");
+  return BOF_OK;
+}
+
+int launch_idx_narrow(bof_ctx* ctx, cudaStream_t s, const int64_t* in, int32_t* out, int64_t n) {
+  if (n == 0) return BOF_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)ctx->num_sms * 16);
+  idx_narrow_kernel<<<grid, 256, 0, s>>>(in, out, n);
+  BOF_LAUNCH_CHECK(ctx, "idx_narrow_kernel");
+  return BOF_OK;
+}
+
+int launch_idx_widen(bof_ctx* ctx, cudaStream_t s, const int32_t* in, int64_t* out, int64_t n) {
+  if (n == 0) return BOF_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)ctx->num_sms * 16);
+  idx_widen_kernel<<<grid, 256, 0, s>>>(in, out, n);
+  BOF_LAUNCH_CHECK(ctx, "idx_widen_kernel");
+  return BOF_OK;
+}
+
+int launch_transpose(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, const float* in,
+                     int64_t ldi, float* out, int64_t ldo) {
+  if (rows == 0 || cols == 0) return BOF_OK;
+  const int64_t tiles_c = ceil_div<int64_t>(cols, 32), tiles_r = ceil_div<int64_t>(rows, 32);
+  BOF_REQUIRE(ctx, tiles_c * tiles_r < (1ll << 31), "transpose: matrix too large for one launch");
+  transpose_kernel<false><<<(unsigned)(tiles_c * tiles_r), 256, 0, s>>>(rows, cols, 1.f, in, ldi, 0.f,
+                                                                       out, ldo, (unsigned)tiles_c);
+  BOF_LAUNCH_CHECK(ctx, "transpose_kernel");
+  return BOF_OK;
+}
+
+int launch_transpose_axpby(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, float alpha,
+                           const float* in, int64_t ldi, float beta, float* out, int64_t ldo) {
+  if (rows == 0 || cols == 0) return BOF_OK;
+  const int64_t tiles_c = ceil_div<int64_t>(cols, 32), tiles_r = ceil_div<int64_t>(rows, 32);
+  BOF_REQUIRE(ctx, tiles_c * tiles_r < (1ll << 31), "transpose: matrix too large for one launch");
+  transpose_kernel<true><<<(unsigned)(tiles_c * tiles_r), 256, 0, s>>>(rows, cols, alpha, in, ldi, beta,
+                                                                      out, ldo, (unsigned)tiles_c);
+  BOF_LAUNCH_CHECK(ctx, "transpose_kernel");
+  return BOF_OK;
+}
+
+}  // namespace bof

@@ -1,0 +1,212 @@
+/*
+ * bof_b200.h -- C ABI of the B200-native replacement for BLAS-on-Flash's tiled hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree, microsoft/BLAS-on-flash).  Three groups:
+ *
+ *   1. context / diagnostics
+ *   2. device-tile kernels: operands already in HBM; `stream` is a cudaStream_t passed as void*
+ *      (replace the per-tile `BaseTask::execute()` bodies, include/tasks/*.h, i.e. the MKL calls)
+ *   3. host entry points: operands in host memory (pageable, pinned or a file mmap, i.e. the
+ *      `flash_ptr<T>::ptr` of include/pointers/pointer.h:15-27); the library streams them through
+ *      pinned staging buffers and CUDA streams (replace src/scheduler/* + src/file_handles/* for
+ *      this path) and the result is in the host buffer when the call returns
+ *      (reference contract: Scheduler::flush_cache() at kernel end, src/blas/gemm.cpp:200).
+ *
+ * Conventions
+ *   - return value: 0 on success, negative on failure (BOF_E*), message via bof_last_error().
+ *     The reference returns FBLAS_INT 0 / -1 (src/blas/csrmm.cpp:433-449); the C++ adapters in
+ *     include/flash_blas.h map any negative code to -1.
+ *   - fp32 values; CSR offsets are int64 (MKL_INT under ILP64, CMakeLists.txt:104); CSR column
+ *     indices are int32 on the device (narrowed while staging) and int64 on the host/file side.
+ *   - one call at a time per context (reference: Cache::flush asserts no active buffers,
+ *     src/scheduler/cache.cpp:45-47).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     BOF_ENODEV.
+ */
+#ifndef BOF_B200_H_
+#define BOF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOF_OK 0
+#define BOF_EINVAL (-1)  /* bad argument (reference: return -1 on bad char, csrmm.cpp:433-449) */
+#define BOF_ECUDA (-2)   /* CUDA runtime/driver error */
+#define BOF_ENOMEM (-3)  /* device or pinned allocation failed */
+#define BOF_ENODEV (-4)  /* no CUDA device / wrong architecture */
+#define BOF_EIO (-5)     /* host I/O failure */
+
+typedef struct bof_ctx bof_ctx;
+
+/* Runtime knobs.  Defaults mirror the reference's compile-time macros (CMakeLists.txt:38-63)
+ * where a counterpart exists.  Zero in any field selects the default. */
+typedef struct bof_config {
+  int32_t device;            /* CUDA ordinal this context drives (one context per GPU/process)  */
+  int32_t n_copy_threads;    /* host staging threads (reference N_IO_THR=4)                     */
+  uint64_t stage_bytes;      /* bytes per pinned staging buffer (default 64 MiB)                */
+  int32_t n_stage_bufs;      /* pinned ring depth per direction (default 4)                     */
+  uint64_t csrmm_max_nnz;    /* nnz budget per streamed CSR row block (reference MAX_NNZS=1e7;
+                                default here 64 Mi so that a block amortises launch latency)    */
+  uint64_t gemm_row_block;   /* rows of A/C per streamed GEMM block (reference GEMM_BLK_SIZE=8192)*/
+  int32_t gemm_k_chunk;      /* k-extent accumulated inside the tensor core before the fp32
+                                round-to-nearest fold (0 = default 512; <0 = whole k)           */
+  int32_t gemm_force_path;   /* 0 auto, 1 tcgen05 1-CTA, 2 tcgen05 2-CTA, 3 CUDA-core FFMA      */
+} bof_config;
+
+/* Per-stage accounting of the last host entry point, for the out-of-core roofline
+ * (no reference counterpart; the reference only logs wall time, drivers/csrmm.cpp:62-65). */
+typedef struct bof_stats {
+  double h2d_bytes, d2h_bytes;      /* bytes that crossed PCIe                                  */
+  double h2d_ms, d2h_ms;            /* CUDA-event time of the copies (summed per stream)        */
+  double kernel_ms;                 /* CUDA-event time of the compute kernels                   */
+  double stage_in_ms, stage_out_ms; /* host memcpy pageable<->pinned (wall, summed over threads)*/
+  double total_ms;                  /* wall time of the call                                    */
+  int64_t kernel_launches;          /* number of this library's kernels launched                */
+} bof_stats;
+
+/* ---- 1. context ----------------------------------------------------------------------- */
+
+/* Replaces the static `flash::sched` + flash_setup() (src/lib_funcs.cpp:9,18-23). */
+int bof_ctx_create(const bof_config* cfg, bof_ctx** out);
+int bof_ctx_destroy(bof_ctx* ctx);
+/* Message of the last failure on this context (ctx may be NULL: last failure of ctx creation). */
+const char* bof_last_error(const bof_ctx* ctx);
+int bof_get_stats(const bof_ctx* ctx, bof_stats* out);
+/* Total kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t bof_launch_count(const bof_ctx* ctx);
+/* ABI version, bumped on any signature change. */
+int bof_abi_version(void);
+
+/* ---- 2. device-tile kernels ------------------------------------------------------------ */
+
+/* K1/K2: C = alpha * A * B + beta * C, A in CSR (m x n), B n x k, C m x k.
+ * Replaces mkl_scsrmm in SimpleCsrmmRmTask::execute (include/tasks/csrmm_task.h:219-228,
+ * ord='R': row-major, 0-based) and SimpleCsrmmCmTask::execute (:290-312, ord='C': column-major;
+ * indices stay 0-based here, the reference's in-place +1 is an MKL calling convention).
+ * beta == 0 => C is not read (csrmm_task.h:194-196).  `offs` may be un-rebased (offs[0] != 0):
+ * vals/idx are indexed by offs[i] - offs[0].  ord='C' needs workspace
+ * bof_spmm_workspace_bytes(); ord='R' needs none. */
+int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n, int64_t k,
+                     float alpha, const float* vals, const int32_t* idx, const int64_t* offs,
+                     const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                     void* workspace, size_t workspace_bytes);
+size_t bof_spmm_workspace_bytes(char ord, int64_t m, int64_t n, int64_t k);
+
+/* K4/K5: y = op(A) x, y overwritten (no alpha/beta).
+ * Replaces mkl_cspblas_scsrgemv in CsrGemvNoTransInMem::execute
+ * (include/tasks/csrgemv_task.h:60-83) and CsrGemvTransInMem::execute (:152-179; the mutex'd
+ * `out[i] += v_out[i]` becomes red.global.add.f32).  trans='N': x has n entries, y has m;
+ * trans='T': x has m entries, y has n and is zeroed by the call (src/blas/csrgemv.cpp:64). */
+int bof_spmv_csr_f32(bof_ctx* ctx, void* stream, char trans, int64_t m, int64_t n,
+                     const float* vals, const int32_t* idx, const int64_t* offs, const float* x,
+                     float* y);
+
+/* Index staging helpers: int64 (file format, misc/sparse_create.cpp:63-81) <-> int32 (device). */
+int bof_idx_narrow(bof_ctx* ctx, void* stream, const int64_t* in, int32_t* out, int64_t count);
+int bof_idx_widen(bof_ctx* ctx, void* stream, const int32_t* in, int64_t* out, int64_t count);
+
+/* K3: C = alpha * op(A) * op(B) + beta * C, fp32 in/out, 3xTF32 on tcgen05 tensor cores.
+ * Replaces cblas_sgemm in GemmTask::execute (include/tasks/gemm_task.h:67-93); argument meaning
+ * as flash::gemm (include/flash_blas.h:14-18): ord 'R'/'C', ta/tb 'N'/'T', ld* = 0 => tight
+ * (src/blas/gemm.cpp:63-67).  beta == 0 => C is not read (gemm_task.h:49-53).
+ * Needs workspace of bof_sgemm_workspace_bytes(m, n, k) bytes (the TF32 hi/lo operand planes). */
+int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb, int64_t m, int64_t n,
+                  int64_t k, float alpha, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, float beta, float* C, int64_t ldc, void* workspace,
+                  size_t workspace_bytes);
+size_t bof_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
+
+/* K6/K7: stable CSR -> CSC (A m x n  ->  A^T as CSR n x m): per output row ascending source
+ * row, duplicates in storage order.  Replaces mkl_scsrcsc + index rebase in
+ * BlockCsrCscTask::execute (include/tasks/csrcsc_task.h:42-92) and the row-block-ordered merge
+ * BlockMergeTask::execute (:136-163).  Atomic-free: radix passes of histogram -> scan -> ranked
+ * scatter.  offs/offs_t int64, idx/idx_t int32.  nnz = offs[m] - offs[0] must be < 2^31. */
+int bof_csr2csc(bof_ctx* ctx, void* stream, int64_t m, int64_t n, int64_t nnz,
+                const int64_t* offs, const int32_t* idx, const float* vals, int64_t* offs_t,
+                int32_t* idx_t, float* vals_t, void* workspace, size_t workspace_bytes);
+size_t bof_csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz);
+
+/* K11: out[r] = sum_j X[r, j]^2 for a row-major rows x dim matrix.
+ * Replaces the cblas_sdot loops of drivers/in_mem_kmeans.cpp:75-78,179-182. */
+int bof_row_sqnorm_f32(bof_ctx* ctx, void* stream, int64_t rows, int64_t dim, const float* X,
+                       int64_t ldx, float* out);
+
+/* K8+K9: assign[p] = first c minimising | fl(fl(-2 <x_p, mu_c> + c_l2sq[c]) + p_l2sq[p]) |.
+ * Replaces KMeansTask::execute (include/tasks/kmeans_task.h:53-82: sgemm alpha=-2 + two rank-1
+ * updates) fused with the cblas_isamin scan of drivers/in_mem_kmeans.cpp:82-85 -- the P x K
+ * distance matrix is never materialised.  points P x dim, centers K x dim, row-major, tight.
+ * Needs workspace bof_kmeans_workspace_bytes(). `points_planes` is optional: a caller iterating
+ * on the same points passes the buffer filled by bof_kmeans_prepare_points() to skip the
+ * per-call TF32 split of the points. */
+int bof_kmeans_assign(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+                      const float* points, const float* centers, const float* c_l2sq,
+                      const float* p_l2sq, int32_t* assign, const void* points_planes,
+                      void* workspace, size_t workspace_bytes);
+size_t bof_kmeans_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim,
+                                  int with_point_planes);
+size_t bof_kmeans_point_planes_bytes(int64_t npoints, int64_t dim);
+int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64_t dim,
+                              const float* points, void* points_planes);
+
+/* K10: sums[c, :] = sum_{p: assign[p]==c} x_p, added sequentially in ascending p (point ids are
+ * grouped by a stable radix sort on the assignment, then one thread block walks each cluster:
+ * deterministic, no atomics), counts[c] = #points.  Replaces the bucket + cblas_saxpy loop of
+ * drivers/in_mem_kmeans.cpp:105-125.  sums is K x dim fp32 followed by nothing; counts K fp32
+ * (exact below 2^24 points per cluster and NCCL-allreduce friendly).  The caller all-reduces
+ * [sums | counts] across GPUs and then calls bof_kmeans_finalize. */
+int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+                      const float* points, const int32_t* assign, float* sums, float* counts,
+                      void* workspace, size_t workspace_bytes);
+size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters);
+/* centers[c] = sums[c] / counts[c], empty cluster => zero vector (in_mem_kmeans.cpp:112);
+ * also refreshes c_l2sq[c] (in_mem_kmeans.cpp:75-78). */
+int bof_kmeans_finalize(bof_ctx* ctx, void* stream, int64_t ncenters, int64_t dim,
+                        const float* sums, const float* counts, float* centers, float* c_l2sq);
+
+/* ---- 3. host entry points (what include/flash_blas.h's adapters call) -------------------- */
+
+/* flash::csrmm (include/flash_blas.h:37-46; src/blas/csrmm.cpp:424-472).  a/ja are indexed
+ * from ia[0]; ja/ia int64 as on disk.  trans_a='T' is csr2csc followed by 'N'. */
+int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha,
+                   float beta, const float* a, const int64_t* ia, const int64_t* ja, char ord_b,
+                   const float* b, float* c);
+
+/* flash::gemm (include/flash_blas.h:14-18; src/blas/gemm.cpp:27-202). */
+int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
+                  float alpha, float beta, const float* a, const float* b, float* c, int64_t lda,
+                  int64_t ldb, int64_t ldc);
+
+/* flash::csrgemv (include/flash_blas.h:55-57; src/blas/csrgemv.cpp:82-97). */
+int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a,
+                     const int64_t* ia, const int64_t* ja, const float* b, float* c);
+
+/* flash::csrcsc (include/flash_blas.h:49-52; src/blas/csrcsc.cpp:32-159). */
+int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const int64_t* ja,
+                    const float* a, int64_t* ia_tr, int64_t* ja_tr, float* a_tr);
+
+/* One Lloyd iteration on this rank's shard of the points, device-resident across calls:
+ * bof_kmeans_open uploads the shard once (drivers/kmeans.cpp:206-217: points mapped, norms
+ * computed once); bof_kmeans_local_step = closest_centers + per-cluster partial sums
+ * (drivers/in_mem_kmeans.cpp:69-125) leaving [K*dim sums | K counts] fp32 in a device buffer
+ * whose address is returned so that the caller can NCCL-allreduce it in place (the only
+ * collective on the path); bof_kmeans_update divides and refreshes the resident centers.
+ * assign_out (host, int64 as FBLAS_UINT center_index, in_mem_kmeans.cpp:82-85) may be NULL. */
+typedef struct bof_kmeans bof_kmeans;
+int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim,
+                    const float* points_host, const float* centers_host, bof_kmeans** out);
+int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_floats);
+int bof_kmeans_update(bof_kmeans* km);
+int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host);
+void* bof_kmeans_stream(bof_kmeans* km);
+int bof_kmeans_close(bof_kmeans* km);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOF_B200_H_ */
