@@ -268,6 +268,8 @@ int bof_ctx_destroy(bof_ctx* ctx) {
   for (int i = 0; i < bof_ctx::kSlots; ++i)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
+  if (ctx->tk0) cudaEventDestroy(ctx->tk0);
+  if (ctx->tk1) cudaEventDestroy(ctx->tk1);
   if (ctx->compute) cudaStreamDestroy(ctx->compute);
   if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
   if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
@@ -280,6 +282,12 @@ const char* bof_last_error(const bof_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int bof_get_stats(const bof_ctx* ctx, bof_stats* out) {
   if (!ctx || !out) return BOF_EINVAL;
   *out = ctx->stats;
+  // kernel_ms: device time of the most recent tensor-core GEMM kernel, once it has finished
+  if (ctx->tk_valid && cudaEventQuery(ctx->tk1) == cudaSuccess) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->tk0, ctx->tk1) == cudaSuccess) out->kernel_ms = ms;
+  }
+  cudaGetLastError();
   return BOF_OK;
 }
 

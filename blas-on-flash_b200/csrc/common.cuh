@@ -48,6 +48,9 @@ struct bof_ctx {
   void* slot_ptr[kSlots] = {};
   size_t slot_bytes[kSlots] = {};
   std::vector<cudaEvent_t> events;
+  // CUDA-event bracket of the most recent tensor-core GEMM kernel (for the roofline figure)
+  cudaEvent_t tk0 = nullptr, tk1 = nullptr;
+  bool tk_valid = false;
 };
 
 namespace bof {

@@ -669,8 +669,15 @@ int launch_variant(bof_ctx* ctx, cudaStream_t s, const CUtensorMap* maps, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (!ctx->tk0) {
+    BOF_CUDA(ctx, cudaEventCreate(&ctx->tk0));
+    BOF_CUDA(ctx, cudaEventCreate(&ctx->tk1));
+  }
+  BOF_CUDA(ctx, cudaEventRecord(ctx->tk0, s));
   BOF_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], prm));
   BOF_LAUNCH_CHECK(ctx, "gemm3xtf32_kernel");
+  BOF_CUDA(ctx, cudaEventRecord(ctx->tk1, s));
+  ctx->tk_valid = true;
   return BOF_OK;
 }
 

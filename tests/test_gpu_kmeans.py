@@ -1,0 +1,111 @@
+"""GPU parity: k-means distance/argmin (fused 3xTF32 GEMM epilogue), centroid reduce, Lloyd iteration."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+G = np.load(Path(__file__).parent / "golden" / "golden_small.npz")
+
+
+def mixture(rng, P, K, d, sigma=0.05, spread=4.0):
+    cent = (rng.normal(size=(K, d)) * spread).astype(np.float32)
+    pts = (cent[rng.integers(0, K, P)] + sigma * rng.normal(size=(P, d))).astype(np.float32)
+    return pts, cent
+
+
+def gpu_assign(ctx, pts, cent):
+    P, d = pts.shape
+    K = cent.shape[0]
+    pd, cd = dev(pts), dev(cent)
+    p2 = torch.empty(P, device="cuda"); c2 = torch.empty(K, device="cuda")
+    ctx.row_sqnorm(P, d, pd, d, p2)
+    ctx.row_sqnorm(K, d, cd, d, c2)
+    out = torch.full((P,), -1, dtype=torch.int32, device="cuda")
+    ctx.kmeans_assign(P, K, d, pd, cd, c2, p2, out)
+    return out.cpu().numpy().astype(np.int64), p2.cpu().numpy(), c2.cpu().numpy()
+
+
+@pytest.mark.parametrize("P,K,d", [(1000, 7, 16), (5000, 1024, 256), (777, 300, 100), (130, 1000, 33), (4096, 256, 64)])
+def test_assign_bit_exact_on_ties_free_points(ctx, P, K, d):
+    rng = np.random.default_rng(P + K + d)
+    pts, cent = mixture(rng, P, K, d)
+    got, p2, c2 = gpu_assign(ctx, pts, cent)
+    assert oracle.rel_fro(p2, oracle.row_sqnorm(pts)) <= TOL and oracle.rel_fro(c2, oracle.row_sqnorm(cent)) <= TOL
+    ref, margin = oracle.kmeans_assign(pts, cent)
+    ok = margin > 1e-3 * (1 + np.abs(p2))  # ties-free: top-2 gap well above fp32 rounding of the distances
+    assert ok.mean() > 0.95
+    assert np.array_equal(got[ok], ref[ok]), f"{(got[ok] != ref[ok]).sum()} mismatches on ties-free points"
+    assert got.min() >= 0 and got.max() < K
+
+
+def test_assign_golden(ctx):
+    pts, cent = G["km_points"], G["km_centers"]
+    got, _, _ = gpu_assign(ctx, pts, cent)
+    _, margin = oracle.kmeans_assign(pts, cent)
+    ok = margin > 1e-3
+    assert np.array_equal(got[ok], G["km_assign"][ok])
+
+
+def test_assign_isamin_semantics(ctx):
+    """first index of the minimum ABSOLUTE value (cblas_isamin, drivers/in_mem_kmeans.cpp:84-85)."""
+    pts = np.zeros((128, 8), np.float32)
+    cent = np.zeros((300, 8), np.float32)
+    cent[:, 0] = 1.0
+    cent[200, 0] = 0.5; cent[260, 0] = 0.5  # two equal minima -> first one wins
+    got, _, _ = gpu_assign(ctx, pts, cent)
+    assert np.all(got == 200)
+    cent[:, 0] = 1.0  # all tie -> index 0
+    got, _, _ = gpu_assign(ctx, pts, cent)
+    assert np.all(got == 0)
+
+
+def test_reduce_and_finalize(ctx):
+    rng = np.random.default_rng(5)
+    P, K, d = 20000, 100, 48
+    pts = rng.normal(size=(P, d)).astype(np.float32)
+    assign = rng.integers(0, K, P).astype(np.int32)
+    assign[assign == 7] = 8  # an empty cluster
+    pd, ad = dev(pts), dev(assign)
+    sums = torch.empty((K, d), device="cuda"); counts = torch.empty(K, device="cuda")
+    ctx.kmeans_reduce(P, K, d, pd, ad, sums, counts)
+    ref_c, ref_n = oracle.kmeans_update(pts, assign.astype(np.int64), K, mode=1)
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), ref_n)
+    # deterministic: same bits on a second run
+    sums2 = torch.empty_like(sums); counts2 = torch.empty_like(counts)
+    ctx.kmeans_reduce(P, K, d, pd, ad, sums2, counts2)
+    assert torch.equal(sums, sums2)
+    cent = torch.empty((K, d), device="cuda"); c2 = torch.empty(K, device="cuda")
+    ctx.kmeans_finalize(K, d, sums, counts, cent, c2)
+    got = cent.cpu().numpy()
+    assert np.all(got[7] == 0)  # empty cluster => zero vector (in_mem_kmeans.cpp:112)
+    assert oracle.rel_fro(got, ref_c) <= TOL
+    assert oracle.rel_fro(got, oracle.kmeans_update(pts, assign.astype(np.int64), K, mode=0)[0]) <= TOL  # reference order
+    assert oracle.rel_fro(c2.cpu().numpy(), oracle.row_sqnorm(got)) <= TOL
+
+
+def test_lloyd_iterations_teacher_forced(bof, ctx):
+    """Each iteration starts from the oracle's centroids of the previous one (hard parts)."""
+    rng = np.random.default_rng(6)
+    P, K, d = 30000, 64, 32
+    pts, cent_true = mixture(rng, P, K, d, sigma=0.3)
+    cent = pts[:K].copy()
+    for it in range(3):
+        km = bof.KMeans(ctx, P, K, d, pts, cent)
+        km.local_step()
+        km.update()
+        got_c = np.zeros((K, d), np.float32); got_a = np.zeros(P, np.int64)
+        km.get(got_c, got_a)
+        km.close()
+        ref_c, ref_a, _ = oracle.lloyd_iter(pts, cent)
+        _, margin = oracle.kmeans_assign(pts, cent)
+        ok = margin > 1e-3 * (1 + np.einsum("ij,ij->i", pts, pts))
+        assert np.array_equal(got_a[ok], ref_a[ok])
+        if ok.all():
+            assert oracle.rel_fro(got_c, ref_c) <= TOL
+        cent = ref_c

@@ -1,0 +1,170 @@
+"""GPU parity: SpMM / SpMV device-tile kernels and the host csrmm / csrgemv pipelines vs the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gpu_util import csr_to_device, dev, ragged_csr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # relative Frobenius error, BASELINE.json north_star
+G = np.load(Path(__file__).parent / "golden" / "golden_small.npz")
+
+
+@pytest.mark.parametrize("k", [4, 8, 32, 64, 100, 128, 256, 260, 1000, 7, 131])
+def test_spmm_rowmajor_k_sweep(ctx, k):
+    rng = np.random.default_rng(k)
+    m, n = 777, 513
+    a, ia, ja = ragged_csr(rng, m, n, 40)
+    B = rng.random((n, k), dtype=np.float32)
+    C0 = rng.random((m, k), dtype=np.float32)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+        Cd = dev(C0 if beta else np.full((m, k), np.nan, np.float32))  # beta == 0: C must not be read
+        ctx.spmm("R", m, n, k, alpha, vals, idx, offs, dev(B), k, beta, Cd, k)
+        ref = oracle.csrmm("N", m, n, k, alpha, beta, a, ia, ja, "R", B, C0, acc64=True)
+        assert oracle.rel_fro(Cd.cpu().numpy(), ref) <= TOL
+
+
+def test_spmm_golden_fixture(ctx):
+    m, n, k = int(G["sp_m"]), int(G["sp_n"]), int(G["sp_k"])
+    vals, idx, offs = csr_to_device(G["sp_a"], G["sp_ia"], G["sp_ja"])
+    Cd = dev(G["sp_C0"])
+    ctx.spmm("R", m, n, k, 1.5, vals, idx, offs, dev(G["sp_B"]), k, 0.5, Cd, k)
+    assert oracle.rel_fro(Cd.cpu().numpy(), G["spmm_R_a15_b05"]) <= TOL
+    # column-major B and C (SimpleCsrmmCmTask)
+    Bc = np.asfortranarray(G["sp_B"]).T.copy().reshape(-1)
+    Cc = dev(np.asfortranarray(G["sp_C0"]).T.copy().reshape(-1))
+    ctx.spmm("C", m, n, k, 1.5, vals, idx, offs, dev(Bc), n, 0.5, Cc, m)
+    assert oracle.rel_fro(Cc.cpu().numpy(), G["spmm_C_a15_b05"]) <= TOL
+
+
+def test_spmm_padded_ld_and_unrebased_offsets(ctx):
+    rng = np.random.default_rng(5)
+    m, n, k = 300, 200, 64
+    a, ia, ja = ragged_csr(rng, m, n, 20)
+    B = np.zeros((n, k + 8), np.float32); B[:, :k] = rng.random((n, k), dtype=np.float32)
+    Cp = np.full((m, k + 4), 7.0, np.float32)
+    r0, r1 = 50, 250
+    z0, z1 = ia[r0], ia[r1]
+    vals, idx, offs = dev(a[z0:z1]), dev(ja[z0:z1].astype(np.int32)), dev(ia[r0:r1 + 1])  # offs[0] != 0
+    Cd = dev(Cp[r0:r1])
+    ctx.spmm("R", r1 - r0, n, k, 1.0, vals, idx, offs, dev(B), k + 8, 0.0, Cd, k + 4)
+    got = Cd.cpu().numpy()
+    ref = oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B[:, :k].copy(), np.zeros((m, k), np.float32), acc64=True)
+    assert oracle.rel_fro(got[:, :k], ref[r0:r1]) <= TOL
+    assert np.all(got[:, k:] == 7.0)  # padding columns untouched
+
+
+def test_spmm_integer_compat_data_bit_exact(ctx):
+    """Reference generator patterns (misc/sparse_create.cpp:52-55, misc/dense_create.cpp:28-32): exact in fp32."""
+    m, n, k = 2048, 1024, 128
+    a, ia, ja = oracle.gen_csr(m, n, 64, seed=1, val_mode=0)
+    B = oracle.gen_dense((n, k), mode=0)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    Cd = torch.empty((m, k), dtype=torch.float32, device="cuda")
+    ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, dev(B), k, 0.0, Cd, k)
+    ref = oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32))
+    assert np.array_equal(Cd.cpu().numpy(), ref)
+
+
+def test_spmm_linearity_at_scale(ctx):
+    """Size-independent property on a cfg-1 shaped slice: A(B1 + 2 B2) == A B1 + 2 A B2 (integer data => exact)."""
+    m, n, k = 65536, 65536, 128
+    a, ia, ja = oracle.gen_csr(m, n, 64, seed=3, val_mode=0)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    B1 = torch.randint(0, 4, (n, k), device="cuda").float()
+    B2 = torch.randint(0, 4, (n, k), device="cuda").float()
+    C1 = torch.empty((m, k), device="cuda"); C2 = torch.empty_like(C1); C3 = torch.empty_like(C1)
+    ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, B1, k, 0.0, C1, k)
+    ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, B2, k, 0.0, C2, k)
+    ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, B1 + 2 * B2, k, 0.0, C3, k)
+    assert torch.equal(C3, C1 + 2 * C2)
+    # and a checksum: sum of C equals sum_j colsum(A)_j * rowsum(B)_j
+    colsum = torch.zeros(n, device="cuda", dtype=torch.float64).index_add_(0, idx.long(), vals.double())
+    assert torch.isclose(C1.double().sum(), (colsum * B1.double().sum(dim=1)).sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("trans", ["N", "T"])
+def test_spmv(ctx, trans):
+    rng = np.random.default_rng(8)
+    m, n = 5000, 3000
+    a, ia, ja = ragged_csr(rng, m, n, 120)
+    x = rng.random(n if trans == "N" else m, dtype=np.float32)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    y = torch.full((m if trans == "N" else n,), float("nan"), device="cuda")
+    ctx.spmv(trans, m, n, vals, idx, offs, dev(x), y)
+    ref = oracle.csrgemv(trans, m, n, a, ia, ja, x, acc64=True)
+    assert oracle.rel_fro(y.cpu().numpy(), ref) <= TOL
+
+
+def test_spmv_golden(ctx):
+    m, n = int(G["sp_m"]), int(G["sp_n"])
+    vals, idx, offs = csr_to_device(G["sp_a"], G["sp_ia"], G["sp_ja"])
+    y = torch.empty(m, device="cuda")
+    ctx.spmv("N", m, n, vals, idx, offs, dev(G["sp_x"]), y)
+    assert oracle.rel_fro(y.cpu().numpy(), G["spmv_N"]) <= TOL
+    yt = torch.empty(n, device="cuda")
+    ctx.spmv("T", m, n, vals, idx, offs, dev(G["sp_xt"]), yt)
+    assert oracle.rel_fro(yt.cpu().numpy(), G["spmv_T"]) <= TOL
+
+
+def test_idx_narrow_widen_roundtrip(ctx):
+    x = torch.randint(0, 2**31 - 1, (100003,), device="cuda", dtype=torch.int64)
+    n32 = torch.empty(x.numel(), device="cuda", dtype=torch.int32)
+    back = torch.empty_like(x)
+    ctx.idx_narrow(x, n32, x.numel())
+    ctx.idx_widen(n32, back, x.numel())
+    assert torch.equal(back, x)
+
+
+@pytest.mark.parametrize("trans,ord_b", [("N", "R"), ("N", "C"), ("T", "R"), ("T", "C")])
+def test_host_csrmm(bof, trans, ord_b):
+    """flash::csrmm through the host entry point; small nnz budget forces several streamed row blocks."""
+    rng = np.random.default_rng(12)
+    m, n, k = 3000, 2000, 96
+    a, ia, ja = ragged_csr(rng, m, n, 50)
+    brows, crows = (n, m) if trans == "N" else (m, n)
+    B = rng.random((brows, k), dtype=np.float32)
+    C0 = rng.random((crows, k), dtype=np.float32)
+    lay = (lambda X: X.copy()) if ord_b == "R" else (lambda X: np.ascontiguousarray(X.T))
+    with bof.Context(device=0, csrmm_max_nnz=20000) as c2:
+        for alpha, beta in ((1.0, 0.0), (0.5, 2.0)):
+            b_h, c_h = lay(B), lay(C0)
+            c2.host_csrmm(trans, m, n, k, alpha, beta, a, ia, ja, ord_b, b_h, c_h)
+            ref = oracle.csrmm(trans, m, n, k, alpha, beta, a, ia, ja, "R", B, C0, acc64=True)
+            got = c_h if ord_b == "R" else c_h.T
+            assert oracle.rel_fro(got, ref) <= TOL, (trans, ord_b, alpha, beta)
+        if trans == "N":
+            assert c2.stats().h2d_bytes > 0 and c2.stats().kernel_launches >= 2
+
+
+def test_host_csrmm_bad_args_return_minus_one(ctx):
+    z = np.zeros(4, np.float32)
+    ia = np.zeros(2, np.int64)
+    lib = ctx.lib
+    from bof_b200 import ptr
+    assert lib.bof_host_csrmm(ctx.h, b"X", 1, 1, 1, 1.0, 0.0, ptr(z), ptr(ia), ptr(ia), b"R", ptr(z), ptr(z)) == -1
+    assert "trans_a" in ctx.last_error()
+    assert lib.bof_host_csrmm(ctx.h, b"N", 1, 1, 1, 1.0, 0.0, ptr(z), ptr(ia), ptr(ia), b"Q", ptr(z), ptr(z)) == -1
+    assert "ord_b" in ctx.last_error()
+
+
+@pytest.mark.parametrize("trans", ["N", "T"])
+def test_host_csrgemv(bof, trans):
+    rng = np.random.default_rng(13)
+    m, n = 4000, 2500
+    a, ia, ja = ragged_csr(rng, m, n, 60)
+    x = rng.random(n if trans == "N" else m, dtype=np.float32)
+    y = np.full(m if trans == "N" else n, np.nan, np.float32)
+    with bof.Context(device=0, csrmm_max_nnz=15000) as c2:
+        c2.host_csrgemv(trans, m, n, a, ia, ja, x, y)
+    assert oracle.rel_fro(y, oracle.csrgemv(trans, m, n, a, ia, ja, x, acc64=True)) <= TOL
+
+
+def test_host_csrmm_empty(ctx):
+    ia = np.zeros(1, np.int64)
+    e = np.zeros(0, np.float32)
+    ctx.host_csrmm("N", 0, 5, 3, 1.0, 0.0, e, ia, np.zeros(0, np.int64), "R", np.zeros((5, 3), np.float32), e)
