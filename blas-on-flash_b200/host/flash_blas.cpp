@@ -1,0 +1,147 @@
+// flash:: adapters over the C ABI (include/bof_b200.h): the C++ host side of the drop-in boundary.
+// Each function flattens its flash_ptr arguments (mmap address of the file, include/pointers/pointer.h)
+// and calls the matching bof_host_* pipeline; nothing here computes.
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "flash_blas.h"
+#include "lib_funcs.h"
+
+namespace flash {
+
+std::string mnt_dir = "./";
+Callback dummy_std_func = [] {};
+
+namespace {
+std::mutex g_mu;
+bof_ctx* g_ctx = nullptr;
+
+int env_device() {
+  for (const char* name : {"BOF_DEVICE", "LOCAL_RANK"})
+    if (const char* v = std::getenv(name)) return std::atoi(v);
+  return 0;
+}
+
+FBLAS_INT done(const char* what, int rc) {
+  if (rc == 0) return 0;
+  std::fprintf(stderr, "[flash::%s] %s\n", what, g_ctx ? bof_last_error(g_ctx) : bof_last_error(nullptr));
+  return -1;
+}
+}  // namespace
+
+bof_ctx* flash_context() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx == nullptr) {
+    bof_config cfg{};
+    cfg.device = env_device();
+    if (bof_ctx_create(&cfg, &g_ctx) != 0) {
+      std::fprintf(stderr, "[flash] cannot create the B200 context: %s\n", bof_last_error(nullptr));
+      g_ctx = nullptr;
+    }
+  }
+  return g_ctx;
+}
+
+void flash_setup(std::string mntdir) {
+  mnt_dir = mntdir;
+  if (!mnt_dir.empty() && mnt_dir.back() != '/') mnt_dir += '/';
+  (void)flash_context();
+}
+
+void flash_destroy() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx) bof_ctx_destroy(g_ctx);
+  g_ctx = nullptr;
+}
+
+FBLAS_INT gemm(CHAR mat_ord, CHAR trans_a, CHAR trans_b, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha,
+               FPTYPE beta, flash_ptr<FPTYPE> a, flash_ptr<FPTYPE> b, flash_ptr<FPTYPE> c, FBLAS_UINT lda_a,
+               FBLAS_UINT lda_b, FBLAS_UINT lda_c) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  return done("gemm", bof_host_gemm(ctx, mat_ord, trans_a, trans_b, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta,
+                                    a.ptr, b.ptr, c.ptr, (int64_t)lda_a, (int64_t)lda_b, (int64_t)lda_c));
+}
+
+FBLAS_INT kmeans(CHAR mat_ord, CHAR trans_a, CHAR trans_b, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha,
+                 FPTYPE beta, flash_ptr<FPTYPE> a, flash_ptr<FPTYPE> b, flash_ptr<FPTYPE> c, FBLAS_UINT lda_a,
+                 FBLAS_UINT lda_b, FBLAS_UINT lda_c, FPTYPE* c_l2sq, FPTYPE* p_l2sq, FPTYPE* /*ones*/) {
+  // KMeansTask::execute (reference include/tasks/kmeans_task.h:68-80): the product, then the two
+  // rank-1 updates C(i, j) += c_l2sq[i] and C(i, j) += p_l2sq[j], in that order.
+  const FBLAS_INT rc = gemm(mat_ord, trans_a, trans_b, m, n, k, alpha, beta, a, b, c, lda_a, lda_b, lda_c);
+  if (rc != 0) return rc;
+  const bool col = mat_ord == 'C';
+  const FBLAS_UINT ld = lda_c ? lda_c : (col ? m : n);
+  FPTYPE* C = c.ptr;
+  for (FBLAS_UINT i = 0; i < m; ++i)
+    for (FBLAS_UINT j = 0; j < n; ++j) {
+      FPTYPE& d = col ? C[j * ld + i] : C[i * ld + j];
+      d = d + c_l2sq[i];
+      d = d + p_l2sq[j];
+    }
+  return 0;
+}
+
+FBLAS_INT csrmm(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha, FPTYPE beta,
+                flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja, CHAR ord_b, flash_ptr<FPTYPE> b,
+                flash_ptr<FPTYPE> c) {
+  return csrmm(trans_a, m, n, k, alpha, beta, a, ia, ja, ord_b, b.ptr, c.ptr);
+}
+
+FBLAS_INT csrmm(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha, FPTYPE beta,
+                flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja, CHAR ord_b, FPTYPE* b, FPTYPE* c) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  return done("csrmm", bof_host_csrmm(ctx, trans_a, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta, a.ptr,
+                                      reinterpret_cast<const int64_t*>(ia.ptr),
+                                      reinterpret_cast<const int64_t*>(ja.ptr), ord_b, b, c));
+}
+
+FBLAS_INT csrcsc(FBLAS_UINT m, FBLAS_UINT n, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja, flash_ptr<FPTYPE> a,
+                 flash_ptr<MKL_INT> ia_tr, flash_ptr<MKL_INT> ja_tr, flash_ptr<FPTYPE> a_tr) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  return done("csrcsc", bof_host_csrcsc(ctx, (int64_t)m, (int64_t)n, reinterpret_cast<const int64_t*>(ia.ptr),
+                                        reinterpret_cast<const int64_t*>(ja.ptr), a.ptr,
+                                        reinterpret_cast<int64_t*>(ia_tr.ptr), reinterpret_cast<int64_t*>(ja_tr.ptr),
+                                        a_tr.ptr));
+}
+
+FBLAS_INT csrgemv(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia,
+                  flash_ptr<MKL_INT> ja, FPTYPE* b, FPTYPE* c) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  return done("csrgemv", bof_host_csrgemv(ctx, trans_a, (int64_t)m, (int64_t)n, a.ptr,
+                                          reinterpret_cast<const int64_t*>(ia.ptr),
+                                          reinterpret_cast<const int64_t*>(ja.ptr), b, c));
+}
+
+FBLAS_INT kmeans_lloyd(flash_ptr<FPTYPE> points, flash_ptr<FPTYPE> centers, FBLAS_UINT npoints, FBLAS_UINT ndims,
+                       FBLAS_UINT ncenters, FBLAS_UINT n_iters, FBLAS_UINT* closest_center,
+                       kmeans_allreduce_fn allreduce, void* allreduce_user) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  bof_kmeans* km = nullptr;
+  int rc = bof_kmeans_open(ctx, (int64_t)npoints, (int64_t)ncenters, (int64_t)ndims, points.ptr, centers.ptr, &km);
+  for (FBLAS_UINT it = 0; rc == 0 && it < n_iters; ++it) {
+    void* partial = nullptr;
+    size_t count = 0;
+    rc = bof_kmeans_local_step(km, &partial, &count);
+    if (rc == 0 && allreduce != nullptr && allreduce(partial, count, bof_kmeans_stream(km), allreduce_user) != 0) {
+      std::fprintf(stderr, "[flash::kmeans_lloyd] allreduce callback failed\n");
+      bof_kmeans_close(km);
+      return -1;
+    }
+    if (rc == 0) rc = bof_kmeans_update(km);
+  }
+  if (rc == 0) {
+    static_assert(sizeof(FBLAS_UINT) == sizeof(int64_t), "assignment buffer is 64-bit");
+    rc = bof_kmeans_get(km, centers.ptr, reinterpret_cast<int64_t*>(closest_center));
+  }
+  if (km) bof_kmeans_close(km);
+  return done("kmeans_lloyd", rc);
+}
+
+}  // namespace flash
