@@ -35,6 +35,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 M_FULL = N_FULL = K_FULL = 32768
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-size gemm3xtf32_kernel launch, from the
+# ncu --set full capture summarised in profiles/ (None until that capture exists)
+NCU_TRAFFIC_BYTES = None
 TILE = 8192  # reference GEMM_BLK_SIZE (CMakeLists.txt:46-50 of the reference)
 
 
@@ -137,6 +140,38 @@ def run_reference(args, rank, world):
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def tf32_library_peak(torch, seconds=3.0):
+    """Roofline denominator only (never on the product path): cuBLAS TF32 8192^3 via torch.matmul,
+    burst = best of 10, sustained = back to back for `seconds` under the power cap -- the same
+    protocol MEASURED_PEAKS.json uses for bf16, which has no TF32 entry."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.rand((n, n), device="cuda"); b = torch.rand((n, n), device="cuda")
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        reps, t_end = 0, time.time() + seconds
+        e0.record()
+        while time.time() < t_end:
+            for _ in range(25):
+                a @ b
+            reps += 25
+            torch.cuda.synchronize()
+        e1.record(); torch.cuda.synchronize()
+        return {"burst": 2.0 * n ** 3 / (best * 1e-3) / 1e12,
+                "sustained": 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def csrmm_extra(bof, ctx, torch, pk):
@@ -243,13 +278,18 @@ def main():
     flops_job = 2.0 * Mg * Ng * Kg
     value = flops_job / t_dev / 1e9
     t_kernel = max_over_ranks(kern_ms[-1] * 1e-3)
-    tf32_third = pk["bf16_sustained"] / 2.0 / 3.0
     achieved = 2.0 * Mr * Ng * Kg / t_kernel / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_third, "unit": "TFLOP/s",
-                "frac": achieved / tf32_third, "traffic": None,
-                "kernel": "gemm3xtf32_kernel<2,0,*>", "kernel_ms": t_kernel * 1e3,
-                "peak_note": f"TF32 dense peak taken as bf16 {pk['src']} sustained {pk['bf16_sustained']} TFLOP/s / 2, "
-                             "divided by 3 for the 3xTF32 split (useful fp32 flops only in the numerator)"}
+    tf32 = tf32_library_peak(torch)
+    # the kernel runs for ~0.3 s per launch under the power cap -> sustained figure; a short debug size -> burst
+    tf32_peak = tf32["sustained"] if t_kernel > 0.05 else tf32["burst"]
+    bf16_sixth = (pk["bf16_sustained"] if t_kernel > 0.05 else pk["bf16_burst"]) / 6.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
+                "frac": achieved / (tf32_peak / 3.0), "traffic": NCU_TRAFFIC_BYTES,
+                "kernel": "gemm3xtf32_kernel<2,EPI_GEMM,chunked>", "kernel_ms": t_kernel * 1e3,
+                "peak_note": "useful fp32 flops (2mnk) against TF32_peak/3; TF32_peak = cuBLAS TF32 8192^3 measured in this "
+                             f"run (burst {tf32['burst']:.0f}, sustained {tf32['sustained']:.0f} TFLOP/s) because "
+                             "MEASURED_PEAKS.json only carries bf16",
+                "alt_peak_bf16_div_6": bf16_sixth, "alt_frac": achieved / bf16_sixth, "peaks_file": pk["src"]}
     # spot check of the result on the timed buffers (cheap: 64 sampled entries in fp64)
     ii = torch.randint(0, Mr, (64,), device="cuda"); jj = torch.randint(0, Ng, (64,), device="cuda")
     ref = (A[ii].double() * B[:, jj].t().double()).sum(1)
