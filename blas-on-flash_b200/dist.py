@@ -1,0 +1,58 @@
+"""Multi-GPU host logic: one process per GPU, output row blocks sharded with no data-path collective;
+the k-means step is the only place with an exchange (allreduce of centroid sums and counts).
+
+Reference context: BLAS-on-Flash is single-process; the shard rule reuses the idea of
+its nnz-budgeted row blocks (include/blas_utils.h:72-97) at the granularity of a rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def row_shard(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous rows [r0, r1) of rank `rank`; sizes differ by at most one row."""
+    base, rem = divmod(n_rows, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def nnz_balanced_shard(ia, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous rows [r0, r1) holding ~nnz/world nonzeros each (CSR offsets `ia`, m+1 entries).
+    Cut points are the first rows whose offset reaches g * nnz / world, so the shards tile [0, m)."""
+    ia = np.asarray(ia)
+    m = ia.shape[0] - 1
+    nnz = int(ia[m] - ia[0])
+    targets = ia[0] + (np.arange(world + 1, dtype=np.int64) * nnz) // world
+    cuts = np.searchsorted(ia, targets, side="left").astype(np.int64)
+    cuts[0], cuts[-1] = 0, m
+    cuts = np.maximum.accumulate(np.minimum(cuts, m))
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
+class DeviceView:
+    """Zero-copy torch view of a raw device buffer returned by the C ABI (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def as_tensor(ptr: int, count: int, device: int):
+    import torch
+
+    return torch.as_tensor(DeviceView(ptr, count), device=f"cuda:{device}")
+
+
+def lloyd(km, iters: int, group=None):
+    """`iters` Lloyd iterations on this rank's resident shard; with a process group the partial
+    [K*dim sums | K counts] buffer is summed in place over NVLink by NCCL on the library's stream."""
+    import torch
+    import torch.distributed as dist
+
+    use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    stream = torch.cuda.ExternalStream(km.stream(), device=km.ctx.device) if use_dist else None
+    for _ in range(iters):
+        ptr, count = km.local_step()
+        if use_dist:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(as_tensor(ptr, count, km.ctx.device), op=dist.ReduceOp.SUM, group=group)
+        km.update()
