@@ -127,7 +127,7 @@ class Context:
 
     def kmeans_reduce(self, npoints, ncenters, dim, points, assign, sums, counts, ws=None, stream=None):
         if ws is None:
-            ws = self._ws(self.lib.bof_kmeans_reduce_workspace_bytes(npoints, ncenters))
+            ws = self._ws(self.lib.bof_kmeans_reduce_workspace_bytes(npoints, ncenters, dim))
         self._check(self.lib.bof_kmeans_reduce(self.h, stream or _cur_stream(), npoints, ncenters, dim, ptr(points),
                                                ptr(assign), ptr(sums), ptr(counts), ptr(ws), ws.numel()))
 

@@ -70,7 +70,7 @@ PROTOTYPES = {
     "bof_kmeans_point_planes_bytes": (_sz, [_i64, _i64]),
     "bof_kmeans_prepare_points": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "bof_kmeans_reduce": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz]),
-    "bof_kmeans_reduce_workspace_bytes": (_sz, [_i64, _i64]),
+    "bof_kmeans_reduce_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "bof_kmeans_finalize": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bof_host_csrmm": (C.c_int, [_vp, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _ch, _vp, _vp]),
     "bof_host_gemm": (C.c_int, [_vp, _ch, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64,

@@ -8,12 +8,78 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 
 using namespace bof;
+
+namespace bof {
+// Minimal fork-join pool for the host side of the staging copies (the reference's N_IO_THR threads).
+class CopyPool {
+ public:
+  explicit CopyPool(int n) {
+    n = std::max(1, n);
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // fn(part) for part in [0, parts); returns when all parts are done.  parts <= size().
+  void run(int parts, const std::function<void(int)>& fn) {
+    if (parts <= 1) { fn(0); return; }
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn; parts_ = parts; pending_ = parts; ++epoch_;
+    cv_.notify_all();
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+        if (id >= parts_) continue;
+        fn = fn_;
+      }
+      (*fn)(id);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int parts_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+}  // namespace bof
 
 namespace {
 
 thread_local std::string g_create_err;
+
+#define BOF_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != BOF_OK) return rc__; \
+  } while (0)
 
 double now_ms() {
   using namespace std::chrono;
@@ -45,17 +111,124 @@ cudaEvent_t get_event(bof_ctx* ctx, size_t i) {
   return ctx->events[i];
 }
 
-// pitched host<->device copy; collapses to a flat copy when both sides are tight
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
+  if (!ring.empty()) return BOF_OK;
+  ring.resize((size_t)ctx->cfg.n_stage_bufs);
+  for (auto& sl : ring) {
+    if (cudaMallocHost(&sl.ptr, ctx->cfg.stage_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, BOF_ENOMEM, "cudaMallocHost of a %llu-byte staging buffer failed",
+                  (unsigned long long)ctx->cfg.stage_bytes);
+    }
+    BOF_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  }
+  if (!ctx->pool) ctx->pool = new CopyPool(ctx->cfg.n_copy_threads);
+  return BOF_OK;
+}
+
+// rows x width bytes between a pitched host matrix and a tightly packed staging slot, split over the pool
+void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_t width, size_t rows, bool to_packed) {
+  const double t0 = now_ms();
+  const size_t total = width * rows;
+  const int parts = (int)std::min<size_t>((size_t)ctx->pool->size(), std::max<size_t>(1, total >> 20));
+  ctx->pool->run(parts, [&](int part) {
+    if (hpitch == width) {  // flat: split by bytes
+      const size_t b0 = total * part / parts, b1 = total * (part + 1) / parts;
+      if (to_packed) std::memcpy(packed + b0, host + b0, b1 - b0);
+      else std::memcpy(host + b0, packed + b0, b1 - b0);
+    } else {
+      const size_t r0 = rows * part / parts, r1 = rows * (part + 1) / parts;
+      for (size_t r = r0; r < r1; ++r) {
+        if (to_packed) std::memcpy(packed + r * width, host + r * hpitch, width);
+        else std::memcpy(host + r * hpitch, packed + r * width, width);
+      }
+    }
+  });
+  (to_packed ? ctx->stats.stage_in_ms : ctx->stats.stage_out_ms) += now_ms() - t0;
+}
+
+int drain_slot(bof_ctx* ctx, StageSlot& sl) {
+  if (!sl.in_flight) return BOF_OK;
+  BOF_CUDA(ctx, cudaEventSynchronize(sl.ev));
+  sl.in_flight = false;
+  if (sl.out_dst) {
+    host_rows_copy(ctx, static_cast<char*>(sl.ptr), sl.out_dst, sl.out_pitch, sl.out_width, sl.out_rows, false);
+    sl.out_dst = nullptr;
+  }
+  return BOF_OK;
+}
+
+// Pageable host memory (e.g. the mmap behind a flash_ptr) <-> device through the pinned ring: the host
+// memcpy of chunk i+1 overlaps the DMA of chunk i.  Blocks the calling thread, like the reference's
+// synchronous FlashFileHandle::read into a cache buffer, but keeps the copy engines at work.
+int staged_copy(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                cudaMemcpyKind kind, cudaStream_t s) {
+  const bool h2d = kind == cudaMemcpyHostToDevice;
+  std::vector<StageSlot>& ring = h2d ? ctx->stage_in : ctx->stage_out;
+  BOF_TRY(ensure_ring(ctx, ring));
+  const size_t cap = ctx->cfg.stage_bytes;
+  // view the transfer as rows of `w` bytes; a flat transfer is cut into cap-sized pseudo rows
+  const bool flat = (dpitch == width && spitch == width) || height == 1;
+  const size_t w = flat ? std::min(cap, width * height) : width;
+  const size_t total_rows = flat ? ceil_div<size_t>(width * height, w) : height;
+  const size_t hp = flat ? w : (h2d ? spitch : dpitch), dp = flat ? w : (h2d ? dpitch : spitch);
+  const size_t rows_per_chunk = std::max<size_t>(1, cap / w);
+  const size_t flat_bytes = width * height;
+  char* host = const_cast<char*>(static_cast<const char*>(h2d ? src : dst));
+  char* dev = const_cast<char*>(static_cast<const char*>(h2d ? dst : src));
+  size_t slot_i = 0;
+  for (size_t r0 = 0; r0 < total_rows; r0 += rows_per_chunk, ++slot_i) {
+    const size_t rows = std::min(rows_per_chunk, total_rows - r0);
+    StageSlot& sl = ring[slot_i % ring.size()];
+    BOF_TRY(drain_slot(ctx, sl));
+    // the last pseudo row of a flat transfer may be short
+    const size_t bytes = flat ? std::min(flat_bytes - r0 * w, rows * w) : rows * w;
+    if (h2d) {
+      if (flat) host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * w, bytes, bytes, 1, true);
+      else host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * hp, hp, w, rows, true);
+      if (flat) BOF_CUDA(ctx, cudaMemcpyAsync(dev + r0 * w, sl.ptr, bytes, kind, s));
+      else BOF_CUDA(ctx, cudaMemcpy2DAsync(dev + r0 * dp, dp, sl.ptr, w, w, rows, kind, s));
+    } else {
+      if (flat) {
+        BOF_CUDA(ctx, cudaMemcpyAsync(sl.ptr, dev + r0 * w, bytes, kind, s));
+        sl.out_dst = host + r0 * w; sl.out_pitch = bytes; sl.out_width = bytes; sl.out_rows = 1;
+      } else {
+        BOF_CUDA(ctx, cudaMemcpy2DAsync(sl.ptr, w, dev + r0 * dp, dp, w, rows, kind, s));
+        sl.out_dst = host + r0 * hp; sl.out_pitch = hp; sl.out_width = w; sl.out_rows = rows;
+      }
+    }
+    BOF_CUDA(ctx, cudaEventRecord(sl.ev, s));
+    sl.in_flight = true;
+  }
+  if (!h2d)
+    for (size_t i = 0; i < ring.size(); ++i) BOF_TRY(drain_slot(ctx, ring[(slot_i + i) % ring.size()]));
+  return BOF_OK;
+}
+
+// pitched host<->device copy; collapses to a flat copy when both sides are tight.  Pinned host memory
+// is copied asynchronously in place; pageable memory goes through the staging ring.
 int copy2d(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
            size_t height, cudaMemcpyKind kind, cudaStream_t s) {
   if (width == 0 || height == 0) return BOF_OK;
+  if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (double)width * height;
+  else if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += (double)width * height;
+  const void* host = kind == cudaMemcpyHostToDevice ? src : dst;
+  const bool staged = width * height >= (256u << 10) && width <= ctx->cfg.stage_bytes && !host_is_pinned(host);
+  if (staged) return staged_copy(ctx, dst, dpitch, src, spitch, width, height, kind, s);
   if (dpitch == width && spitch == width) {
     BOF_CUDA(ctx, cudaMemcpyAsync(dst, src, width * height, kind, s));
   } else {
     BOF_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s));
   }
-  if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (double)width * height;
-  else if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += (double)width * height;
   return BOF_OK;
 }
 int copy1d(bof_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
@@ -79,11 +252,6 @@ int sync_all(bof_ctx* ctx) {
   return BOF_OK;
 }
 
-#define BOF_TRY(expr)          \
-  do {                         \
-    int rc__ = (expr);         \
-    if (rc__ != BOF_OK) return rc__; \
-  } while (0)
 
 // Canonical form of a GEMM: Cout[Mo x No] (row-major, ldc) = P[Mo x K] * Q[No x K]^T where
 // element (r, kk) of P is psrc[r*p_sr + kk*p_sk] (one of the strides is 1), same for Q.
@@ -140,7 +308,7 @@ int pick_gemm_path(const bof_ctx* ctx, int64_t Mo, int64_t No, int64_t K) {
 
 int64_t k_chunk_of(const bof_ctx* ctx) {
   if (ctx->cfg.gemm_k_chunk < 0) return 0;
-  return ctx->cfg.gemm_k_chunk == 0 ? 512 : ctx->cfg.gemm_k_chunk;
+  return ctx->cfg.gemm_k_chunk == 0 ? 256 : ctx->cfg.gemm_k_chunk;
 }
 
 // GEMM on device-resident canonical operands with a caller-provided plane workspace.
@@ -243,7 +411,7 @@ int bof_ctx_create(const bof_config* cfg, bof_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
   if (ctx->cfg.n_copy_threads <= 0) ctx->cfg.n_copy_threads = 4;
-  if (ctx->cfg.stage_bytes == 0) ctx->cfg.stage_bytes = 64ull << 20;
+  if (ctx->cfg.stage_bytes == 0) ctx->cfg.stage_bytes = 16ull << 20;
   if (ctx->cfg.n_stage_bufs <= 0) ctx->cfg.n_stage_bufs = 4;
   if (ctx->cfg.csrmm_max_nnz == 0) ctx->cfg.csrmm_max_nnz = 64ull << 20;
   if (ctx->cfg.gemm_row_block == 0) ctx->cfg.gemm_row_block = 4096;
@@ -268,6 +436,12 @@ int bof_ctx_destroy(bof_ctx* ctx) {
   for (int i = 0; i < bof_ctx::kSlots; ++i)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
+  for (auto* ring : {&ctx->stage_in, &ctx->stage_out})
+    for (auto& sl : *ring) {
+      if (sl.ptr) cudaFreeHost(sl.ptr);
+      if (sl.ev) cudaEventDestroy(sl.ev);
+    }
+  delete ctx->pool;
   if (ctx->tk0) cudaEventDestroy(ctx->tk0);
   if (ctx->tk1) cudaEventDestroy(ctx->tk1);
   if (ctx->compute) cudaStreamDestroy(ctx->compute);
@@ -425,8 +599,8 @@ int bof_kmeans_assign(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncent
                         reinterpret_cast<const float*>(pp + plane_bytes(npoints, kp)), c_hi, c_lo, ep, 0);
 }
 
-size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters) {
-  return kmeans_reduce_workspace_bytes(npoints, ncenters);
+size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim) {
+  return kmeans_reduce_workspace_bytes(npoints, ncenters, dim);
 }
 
 int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
@@ -560,9 +734,11 @@ int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, 
     BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)max_rows * k, &cblk[g]));
     if (colmaj) BOF_TRY(slot_reserve(ctx, S_CBLK_T + g, (size_t)max_rows * k, &cblk_t[g]));
   }
-  // events: 4+g uploaded, 6+g computed, 8+g downloaded
+  // events: 4+g uploaded, 6+g computed, 8+g downloaded.  Software-pipelined issue order: block i+1 is
+  // uploaded and launched before block i is downloaded, so a (host-blocking) staged download of
+  // block i overlaps the kernel of block i+1 and the copy engines never wait on the host.
   bool used[2] = {false, false};
-  for (int i = 0; i < nblk; ++i) {
+  auto stage_block = [&](int i) -> int {
     const int g = i & 1;
     const int64_t r0 = cuts[i], r1 = cuts[i + 1], rows = r1 - r0;
     const int64_t z0 = offs_host[r0] - offs_host[0], z1 = offs_host[r1] - offs_host[0], bnnz = z1 - z0;
@@ -590,11 +766,23 @@ int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, 
       BOF_TRY(launch_spmm_rm(ctx, ctx->compute, rows, k, alpha, vals_d[g], idx32_d[g], offs_d[g], Bd, k, beta, cblk[g], k));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ev_done, 0));
+    used[g] = true;
+    return BOF_OK;
+  };
+  auto fetch_block = [&](int i) -> int {
+    const int g = i & 1;
+    const int64_t r0 = cuts[i], rows = cuts[i + 1] - r0;
+    float* c_io = colmaj ? cblk_t[g] : cblk[g];
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, 6 + g), 0));
     if (colmaj) BOF_TRY(copy2d(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, D2H, ctx->d2h));
     else BOF_TRY(copy1d(ctx, c + r0 * k, c_io, (size_t)rows * k * 4, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(ev_down, ctx->d2h));
-    used[g] = true;
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->d2h));
+    return BOF_OK;
+  };
+  if (nblk > 0) BOF_TRY(stage_block(0));
+  for (int i = 0; i < nblk; ++i) {
+    if (i + 1 < nblk) BOF_TRY(stage_block(i + 1));
+    BOF_TRY(fetch_block(i));
   }
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
@@ -662,7 +850,8 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)rb * cn.No, &cblk[g]));
   }
   bool used[2] = {false, false};
-  for (int i = 0; i < nblk; ++i) {
+  // same software-pipelined order as bof_host_csrmm: stage block i+1, then fetch block i
+  auto stage_block = [&](int i) -> int {
     const int g = i & 1;
     const int64_t r0 = (int64_t)i * rb, r1 = std::min(cn.Mo, r0 + rb), rows = r1 - r0;
     cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_split = get_event(ctx, 6 + g), ev_done = get_event(ctx, 8 + g),
@@ -692,10 +881,21 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
                                cblk[g], cn.No));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ev_done, 0));
-    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk[g], (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(ev_down, ctx->d2h));
     used[g] = true;
+    return BOF_OK;
+  };
+  auto fetch_block = [&](int i) -> int {
+    const int g = i & 1;
+    const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, 8 + g), 0));
+    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk[g], (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 10 + g), ctx->d2h));
+    return BOF_OK;
+  };
+  if (nblk > 0) BOF_TRY(stage_block(0));
+  for (int i = 0; i < nblk; ++i) {
+    if (i + 1 < nblk) BOF_TRY(stage_block(i + 1));
+    BOF_TRY(fetch_block(i));
   }
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
@@ -850,7 +1050,7 @@ int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim
   km->ctx = ctx; km->npoints = npoints; km->ncenters = ncenters; km->dim = dim;
   const size_t P = (size_t)std::max<int64_t>(npoints, 1);
   km->ws_assign_bytes = bof_kmeans_workspace_bytes(npoints, ncenters, dim, 0);
-  km->ws_reduce_bytes = kmeans_reduce_workspace_bytes(npoints, ncenters);
+  km->ws_reduce_bytes = kmeans_reduce_workspace_bytes(npoints, ncenters, dim);
   struct Req { void** p; size_t bytes; } reqs[] = {
       {(void**)&km->points, P * dim * 4}, {&km->point_planes, bof_kmeans_point_planes_bytes(npoints, dim)},
       {(void**)&km->p_l2sq, P * 4}, {(void**)&km->centers, (size_t)ncenters * dim * 4},

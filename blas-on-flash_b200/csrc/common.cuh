@@ -19,10 +19,17 @@ namespace bof {
 
 constexpr int kNumSmsFallback = 148;
 
-struct PinnedBuf {
+// One slot of the pinned staging ring used for pageable host operands (file mmaps).
+struct StageSlot {
   void* ptr = nullptr;
-  size_t bytes = 0;
+  cudaEvent_t ev = nullptr;   // completion of the DMA that last used the slot
+  bool in_flight = false;
+  // pending device->host chunk: where the slot's contents go once the DMA has landed
+  char* out_dst = nullptr;
+  size_t out_pitch = 0, out_width = 0, out_rows = 0;
 };
+
+class CopyPool;  // host memcpy worker threads (capi.cu)
 
 }  // namespace bof
 
@@ -36,7 +43,8 @@ struct bof_ctx {
   cudaStream_t compute = nullptr;  // kernels of the host entry points
   cudaStream_t h2d = nullptr;      // uploads
   cudaStream_t d2h = nullptr;      // downloads
-  std::vector<bof::PinnedBuf> stage_in, stage_out;
+  std::vector<bof::StageSlot> stage_in, stage_out;   // pinned rings, allocated on first pageable copy
+  bof::CopyPool* pool = nullptr;
   std::string err;
   bof_stats stats{};
   std::atomic<int64_t> launches{0};
@@ -157,7 +165,7 @@ int launch_gemm_ffma(bof_ctx* ctx, cudaStream_t s, int64_t M, int64_t N, int64_t
 
 int launch_row_sqnorm(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t dim, const float* X,
                       int64_t ldx, float* out);
-size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters);
+size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim);
 int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
                             int64_t dim, const float* points, const int32_t* assign, float* sums,
                             float* counts, void* ws, size_t ws_bytes);

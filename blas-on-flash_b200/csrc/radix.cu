@@ -22,10 +22,10 @@
 namespace bof {
 namespace {
 
-constexpr int RS_THREADS = 512;
+constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = 16;                       // items per thread
-constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 8192 items per tile
+constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 4096 items per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_CNT_STRIDE = RS_BINS + 1;       // +1: sentinel bin for out-of-range items
 
@@ -33,6 +33,20 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// Lanes of the warp holding the same 9-bit digit (8 data bits + the out-of-range sentinel bit).
+// Nine ballots and a few logic ops: MATCH.ANY measured ~10x slower than this on sm_100
+// (profiles/r01: radix_hist_kernel was issue-bound at 96% SM throughput with __match_any_sync).
+__device__ __forceinline__ unsigned digit_peers(uint32_t d) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
 }
 
 // counts[digit * num_tiles + tile] = number of keys of the tile whose digit is `digit`
@@ -48,7 +62,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
   for (int r = 0; r < RS_IPT; ++r) {
     const int64_t i = warp_base + r * 32 + lane;
     const uint32_t d = (i < n) ? ((__ldcs(keys + i) >> shift) & 255u) : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned peers = digit_peers(d);
     if ((peers & lanemask_lt()) == 0) cnt[warp][d] += __popc(peers);  // one writer per digit
     __syncwarp();
   }
@@ -71,7 +85,7 @@ struct ScatterSmem {
 
 // Stable scatter of one tile.  offsets = exclusive scan of the histogram kernel's counts.
 // Moves the key and up to two 32-bit payloads.
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                      const uint32_t* __restrict__ p1_in, uint32_t* __restrict__ p1_out,
                      const uint32_t* __restrict__ p2_in, uint32_t* __restrict__ p2_out, int64_t n,
@@ -87,21 +101,26 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
   const int64_t warp_base = tile_base + (int64_t)warp * 32 * RS_IPT;
   const int tile_count = (int)min((int64_t)RS_TILE, n - tile_base);
 
+  // per item: the key and its rank (later: its slot in the block-sorted tile); digits are recomputed
   uint32_t key[RS_IPT];
-  uint16_t rank[RS_IPT];
-  uint16_t dig[RS_IPT];
+  uint32_t slot[RS_IPT];
+  auto digit_of = [&](int r) -> uint32_t {
+    return (warp_base + r * 32 + lane < n) ? ((key[r] >> shift) & 255u) : 256u;
+  };
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
     const int64_t i = warp_base + r * 32 + lane;
     key[r] = (i < n) ? __ldcs(keys_in + i) : 0u;
-    const uint32_t d = (i < n) ? ((key[r] >> shift) & 255u) : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+  }
+#pragma unroll
+  for (int r = 0; r < RS_IPT; ++r) {
+    const uint32_t d = digit_of(r);
+    const unsigned peers = digit_peers(d);
     const uint32_t old = sm.cnt[warp][d];
     __syncwarp();
     if ((peers & lanemask_lt()) == 0) sm.cnt[warp][d] = old + __popc(peers);
     __syncwarp();
-    rank[r] = (uint16_t)(old + __popc(peers & lanemask_lt()));
-    dig[r] = (uint16_t)d;
+    slot[r] = old + __popc(peers & lanemask_lt());
   }
   __syncthreads();
 
@@ -115,7 +134,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
       total += t;
     }
   }
-  // block-wide exclusive scan of `total` over the first 256 threads (8 warps)
+  // block-wide exclusive scan of `total` (one digit per thread)
   {
     uint32_t incl = total;
 #pragma unroll
@@ -133,19 +152,19 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
   }
   __syncthreads();
 
-  uint16_t pos[RS_IPT];
+  constexpr uint32_t NO_SLOT = 0xffffffffu;
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r) {
-    const uint32_t d = dig[r];
-    pos[r] = (d < 256u) ? (uint16_t)(sm.digit_off[d] + sm.cnt[warp][d] + rank[r]) : (uint16_t)0xffff;
+    const uint32_t d = digit_of(r);
+    slot[r] = (d < 256u) ? sm.digit_off[d] + sm.cnt[warp][d] + slot[r] : NO_SLOT;
   }
 
   // keys: local sort into smem, then contiguous runs to global
 #pragma unroll
   for (int r = 0; r < RS_IPT; ++r)
-    if (pos[r] != 0xffff) {
-      sm.stage[pos[r]] = key[r];
-      sm.sdig[pos[r]] = dig[r];
+    if (slot[r] != NO_SLOT) {
+      sm.stage[slot[r]] = key[r];
+      sm.sdig[slot[r]] = (uint16_t)((key[r] >> shift) & 255u);
     }
   __syncthreads();
   for (int s = threadIdx.x; s < tile_count; s += RS_THREADS) {
@@ -153,21 +172,21 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     keys_out[(size_t)sm.gbase[d] + (s - sm.digit_off[d])] = sm.stage[s];
   }
   // payloads reuse the staging buffer
-  const uint32_t* pin[2] = {p1_in, p2_in};
-  uint32_t* pout[2] = {p1_out, p2_out};
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    if (pin[q] == nullptr) continue;
+    const uint32_t* pin = q == 0 ? p1_in : p2_in;
+    uint32_t* pout = q == 0 ? p1_out : p2_out;
+    if (pin == nullptr) continue;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RS_IPT; ++r) {
       const int64_t i = warp_base + r * 32 + lane;
-      if (pos[r] != 0xffff) sm.stage[pos[r]] = __ldcs(pin[q] + i);
+      if (slot[r] != NO_SLOT) sm.stage[slot[r]] = __ldcs(pin + i);
     }
     __syncthreads();
     for (int s = threadIdx.x; s < tile_count; s += RS_THREADS) {
       const uint32_t d = sm.sdig[s];
-      pout[q][(size_t)sm.gbase[d] + (s - sm.digit_off[d])] = sm.stage[s];
+      pout[(size_t)sm.gbase[d] + (s - sm.digit_off[d])] = sm.stage[s];
     }
   }
 }
@@ -348,33 +367,87 @@ row_sqnorm_kernel(int64_t rows, int64_t dim, const float* __restrict__ X, int64_
   if (lane == 0) out[row] = acc;
 }
 
-// One block per cluster: sums[c, j] = sum of x_p[j] over the cluster's points in ascending p
-// (sequential fp32 adds: deterministic, same order as the reference's saxpy loop).
-__global__ void __launch_bounds__(256)
-kmeans_segment_sum_kernel(int64_t dim, const float* __restrict__ points,
-                          const uint32_t* __restrict__ sorted_ids, const float* __restrict__ seg_offs_f,
-                          const int64_t* __restrict__ seg_offs, float* __restrict__ sums,
-                          float* __restrict__ counts) {
-  (void)seg_offs_f;
-  const int64_t c = blockIdx.x;
-  const int64_t beg = seg_offs[c], end = seg_offs[c + 1];
-  for (int64_t j0 = 0; j0 < dim; j0 += blockDim.x) {
-    const int64_t j = j0 + threadIdx.x;
-    float acc = 0.f;
-    if (j < dim) {
-      int64_t i = beg;
-      for (; i + 8 <= end; i += 8) {
-        float v[8];
+// Centroid partial sums, load-balanced and deterministic.  Clusters are cut into segments of KM_SEG
+// points of the id list sorted by (cluster, p); one block sums one segment (one thread per
+// dimension, sequential fp32 adds in ascending p, 8 row loads in flight), a second kernel adds the
+// segments of each cluster in ascending order.  A 15x cluster-size imbalance (seen on cfg-5) no
+// longer serialises behind one block.
+constexpr int KM_SEG = 256;
+
+// seg_base[c] = number of segments of clusters < c (exclusive scan of ceil(count_c / KM_SEG)); one block
+__global__ void __launch_bounds__(1024)
+kmeans_plan_kernel(int64_t ncenters, const int64_t* __restrict__ seg_offs, int32_t* __restrict__ seg_base) {
+  __shared__ int32_t wsum[32];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t c0 = 0; c0 < ncenters; c0 += blockDim.x) {
+    const int64_t c = c0 + threadIdx.x;
+    const int32_t v = (c < ncenters) ? (int32_t)((seg_offs[c + 1] - seg_offs[c] + KM_SEG - 1) / KM_SEG) : 0;
+    int32_t incl = v;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(points + (int64_t)sorted_ids[i + u] * dim + j);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
-      }
-      for (; i < end; ++i) acc += __ldcs(points + (int64_t)sorted_ids[i] * dim + j);
-      sums[c * dim + j] = acc;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int32_t add = carry_s;
+    for (int w = 0; w < warp; ++w) add += wsum[w];
+    if (c < ncenters) seg_base[c] = add + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = add + incl;
+    __syncthreads();
   }
-  if (threadIdx.x == 0) counts[c] = (float)(end - beg);
+  if (threadIdx.x == 0) seg_base[ncenters] = carry_s;
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_partial_kernel(int64_t ncenters, int64_t dim, const float* __restrict__ points,
+                      const uint32_t* __restrict__ sorted_ids, const int64_t* __restrict__ seg_offs,
+                      const int32_t* __restrict__ seg_base, float* __restrict__ partial) {
+  __shared__ int64_t s_beg, s_end;
+  const int32_t b = blockIdx.x;
+  if (b >= seg_base[ncenters]) return;
+  if (threadIdx.x == 0) {
+    int64_t lo = 0, hi = ncenters;  // last c with seg_base[c] <= b
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (seg_base[mid] <= b) lo = mid; else hi = mid;
+    }
+    const int64_t beg = seg_offs[lo] + (int64_t)(b - seg_base[lo]) * KM_SEG;
+    s_beg = beg;
+    s_end = min(seg_offs[lo + 1], beg + KM_SEG);
+  }
+  __syncthreads();
+  const int64_t beg = s_beg, end = s_end;
+  for (int64_t j = threadIdx.x; j < dim; j += blockDim.x) {
+    float acc = 0.f;
+    int64_t i = beg;
+    for (; i + 8 <= end; i += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(points + (int64_t)sorted_ids[i + u] * dim + j);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; i < end; ++i) acc += __ldcs(points + (int64_t)sorted_ids[i] * dim + j);
+    partial[(int64_t)b * dim + j] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_combine_kernel(int64_t dim, const float* __restrict__ partial, const int64_t* __restrict__ seg_offs,
+                      const int32_t* __restrict__ seg_base, float* __restrict__ sums, float* __restrict__ counts) {
+  const int64_t c = blockIdx.x;
+  const int32_t s0 = seg_base[c], s1 = seg_base[c + 1];
+  for (int64_t j = threadIdx.x; j < dim; j += blockDim.x) {
+    float acc = 0.f;
+    for (int32_t sgm = s0; sgm < s1; ++sgm) acc += partial[(int64_t)sgm * dim + j];
+    sums[c * dim + j] = acc;
+  }
+  if (threadIdx.x == 0) counts[c] = (float)(seg_offs[c + 1] - seg_offs[c]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -465,9 +538,12 @@ int launch_row_sqnorm(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t dim, c
   return BOF_OK;
 }
 
-size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters) {
+static int64_t km_max_segments(int64_t npoints, int64_t ncenters) { return npoints / KM_SEG + ncenters + 1; }
+
+size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim) {
   const size_t arr = align_up((size_t)std::max<int64_t>(npoints, 1) * 4);
-  return 4 * arr + counts_bytes(npoints) + align_up((size_t)(ncenters + 1) * 8) + 256;
+  return 4 * arr + counts_bytes(npoints) + align_up((size_t)(ncenters + 1) * 8) + align_up((size_t)(ncenters + 1) * 4) +
+         align_up((size_t)km_max_segments(npoints, ncenters) * (size_t)std::max<int64_t>(dim, 1) * 4) + 256;
 }
 
 int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
@@ -475,7 +551,7 @@ int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64
                             float* counts_out, void* ws, size_t ws_bytes) {
   BOF_REQUIRE(ctx, npoints < (1ll << 31) && ncenters < (1ll << 31), "kmeans_reduce: extents must be below 2^31");
   BOF_REQUIRE(ctx, ncenters > 0 && dim > 0, "kmeans_reduce: empty problem");
-  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= kmeans_reduce_workspace_bytes(npoints, ncenters),
+  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= kmeans_reduce_workspace_bytes(npoints, ncenters, dim),
               "kmeans_reduce: workspace too small");
   const size_t arr = align_up((size_t)std::max<int64_t>(npoints, 1) * 4);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
@@ -483,6 +559,8 @@ int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64
   Triple Y{reinterpret_cast<uint32_t*>(base + 2 * arr), reinterpret_cast<uint32_t*>(base + 3 * arr), nullptr};
   uint32_t* counts = reinterpret_cast<uint32_t*>(base + 4 * arr);
   int64_t* seg = reinterpret_cast<int64_t*>(base + 4 * arr + counts_bytes(npoints));
+  int32_t* seg_base = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(seg) + align_up((size_t)(ncenters + 1) * 8));
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(seg_base) + align_up((size_t)(ncenters + 1) * 4));
 
   const uint32_t* kin = reinterpret_cast<const uint32_t*>(assign);
   const uint32_t* pin = nullptr;
@@ -504,8 +582,13 @@ int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(npoints + 1, 256), (int64_t)ctx->num_sms * 32);
   segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(kin, npoints, ncenters, seg);
   BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
-  kmeans_segment_sum_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, points, pin, nullptr, seg, sums, counts_out);
-  BOF_LAUNCH_CHECK(ctx, "kmeans_segment_sum_kernel");
+  kmeans_plan_kernel<<<1, 1024, 0, s>>>(ncenters, seg, seg_base);
+  BOF_LAUNCH_CHECK(ctx, "kmeans_plan_kernel");
+  kmeans_partial_kernel<<<(unsigned)km_max_segments(npoints, ncenters), 256, 0, s>>>(ncenters, dim, points, pin, seg,
+                                                                                     seg_base, partial);
+  BOF_LAUNCH_CHECK(ctx, "kmeans_partial_kernel");
+  kmeans_combine_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, partial, seg, seg_base, sums, counts_out);
+  BOF_LAUNCH_CHECK(ctx, "kmeans_combine_kernel");
   return BOF_OK;
 }
 

@@ -160,8 +160,9 @@ spmm_csr_rm_generic_kernel(int64_t m, int64_t k, float alpha, const float* __res
   }
 }
 
-// y = A x : L lanes per row, shuffle reduction inside the group.
-template <int L>
+// y = A x : L lanes per row, U nonzeros per lane in flight (the (col, val) stream and the dependent
+// x gathers need ~44 KB outstanding per SM to cover HBM latency), shuffle reduction inside the group.
+template <int L, int U>
 __global__ void __launch_bounds__(256)
 spmv_csr_n_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __restrict__ idx,
                   const int64_t* __restrict__ offs, const float* __restrict__ x,
@@ -178,7 +179,20 @@ spmv_csr_n_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __re
     end = offs[row + 1] - base;
   }
   float acc = 0.f;
-  for (int64_t j = beg + sl; j < end; j += L) acc = fmaf(__ldcs(vals + j), __ldg(x + __ldcs(idx + j)), acc);
+  for (int64_t j = beg + sl; j < end; j += L * U) {
+    int32_t c[U];
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t jj = j + u * L;
+      const bool ok = jj < end;
+      c[u] = ok ? __ldcs(idx + jj) : -1;
+      v[u] = ok ? __ldcs(vals + jj) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c[u] >= 0) acc = fmaf(v[u], __ldg(x + c[u]), acc);
+  }
 #pragma unroll
   for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, L);
   if (row < m && sl == 0) y[row] = acc;
@@ -186,7 +200,7 @@ spmv_csr_n_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __re
 
 // y += A^T x : every nonzero (r, c, v) contributes v * x[r] to y[c]; red.global.add.f32
 // replaces the reference's mutex-serialised vector add (csrgemv_task.h:170-176).
-template <int L>
+template <int L, int U>
 __global__ void __launch_bounds__(256)
 spmv_csr_t_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __restrict__ idx,
                   const int64_t* __restrict__ offs, const float* __restrict__ x,
@@ -200,7 +214,20 @@ spmv_csr_t_kernel(int64_t m, const float* __restrict__ vals, const int32_t* __re
   const int64_t base = offs[0];
   const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
   const float xr = __ldg(x + row);
-  for (int64_t j = beg + sl; j < end; j += L) atomicAdd(y + __ldcs(idx + j), __ldcs(vals + j) * xr);
+  for (int64_t j = beg + sl; j < end; j += L * U) {
+    int32_t c[U];
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t jj = j + u * L;
+      const bool ok = jj < end;
+      c[u] = ok ? __ldcs(idx + jj) : -1;
+      v[u] = ok ? __ldcs(vals + jj) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c[u] >= 0) atomicAdd(y + c[u], v[u] * xr);
+  }
 }
 
 __global__ void idx_narrow_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out,
@@ -290,12 +317,12 @@ int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, 
   if (trans == 'T' || trans == 't') {
     if (trans == 'T') BOF_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s));
     if (m == 0) return BOF_OK;
-    spmv_csr_t_kernel<16><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
+    spmv_csr_t_kernel<16, 4><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
     BOF_LAUNCH_CHECK(ctx, "spmv_csr_t_kernel");
     return BOF_OK;
   }
   if (m == 0) return BOF_OK;
-  spmv_csr_n_kernel<16><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
+  spmv_csr_n_kernel<16, 4><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
   BOF_LAUNCH_CHECK(ctx, "spmv_csr_n_kernel");
   return BOF_OK;
 }

@@ -49,13 +49,13 @@ typedef struct bof_ctx bof_ctx;
 typedef struct bof_config {
   int32_t device;            /* CUDA ordinal this context drives (one context per GPU/process)  */
   int32_t n_copy_threads;    /* host staging threads (reference N_IO_THR=4)                     */
-  uint64_t stage_bytes;      /* bytes per pinned staging buffer (default 64 MiB)                */
+  uint64_t stage_bytes;      /* bytes per pinned staging buffer (default 16 MiB)                */
   int32_t n_stage_bufs;      /* pinned ring depth per direction (default 4)                     */
   uint64_t csrmm_max_nnz;    /* nnz budget per streamed CSR row block (reference MAX_NNZS=1e7;
                                 default here 64 Mi so that a block amortises launch latency)    */
   uint64_t gemm_row_block;   /* rows of A/C per streamed GEMM block (reference GEMM_BLK_SIZE=8192)*/
   int32_t gemm_k_chunk;      /* k-extent accumulated inside the tensor core before the fp32
-                                round-to-nearest fold (0 = default 512; <0 = whole k)           */
+                                round-to-nearest fold (0 = default 256; <0 = whole k)           */
   int32_t gemm_force_path;   /* 0 auto, 1 tcgen05 1-CTA, 2 tcgen05 2-CTA, 3 CUDA-core FFMA      */
 } bof_config;
 
@@ -155,15 +155,15 @@ int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64
                               const float* points, void* points_planes);
 
 /* K10: sums[c, :] = sum_{p: assign[p]==c} x_p, added sequentially in ascending p (point ids are
- * grouped by a stable radix sort on the assignment, then one thread block walks each cluster:
- * deterministic, no atomics), counts[c] = #points.  Replaces the bucket + cblas_saxpy loop of
+ * grouped by a stable radix sort on the assignment, then fixed 256-point segments of each cluster
+ * are summed by one thread block each and combined in order: deterministic, no atomics), counts[c] = #points.  Replaces the bucket + cblas_saxpy loop of
  * drivers/in_mem_kmeans.cpp:105-125.  sums is K x dim fp32 followed by nothing; counts K fp32
  * (exact below 2^24 points per cluster and NCCL-allreduce friendly).  The caller all-reduces
  * [sums | counts] across GPUs and then calls bof_kmeans_finalize. */
 int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
                       const float* points, const int32_t* assign, float* sums, float* counts,
                       void* workspace, size_t workspace_bytes);
-size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters);
+size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim);
 /* centers[c] = sums[c] / counts[c], empty cluster => zero vector (in_mem_kmeans.cpp:112);
  * also refreshes c_l2sq[c] (in_mem_kmeans.cpp:75-78). */
 int bof_kmeans_finalize(bof_ctx* ctx, void* stream, int64_t ncenters, int64_t dim,
