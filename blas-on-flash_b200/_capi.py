@@ -26,6 +26,8 @@ class BofConfig(C.Structure):
         ("gemm_row_block", C.c_uint64),
         ("gemm_k_chunk", C.c_int32),
         ("gemm_force_path", C.c_int32),
+        ("gemm_wave_sync", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

@@ -442,6 +442,7 @@ int bof_ctx_destroy(bof_ctx* ctx) {
       if (sl.ev) cudaEventDestroy(sl.ev);
     }
   delete ctx->pool;
+  if (ctx->sync_ctr) cudaFree(ctx->sync_ctr);
   if (ctx->tk0) cudaEventDestroy(ctx->tk0);
   if (ctx->tk1) cudaEventDestroy(ctx->tk1);
   if (ctx->compute) cudaStreamDestroy(ctx->compute);
@@ -806,8 +807,9 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
   const int path = pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
   const int64_t K = cn.K, kp = padded_k(K);
   const bool tensor = (K > 0 && path != 3);
+  const int cg = path == 1 ? 1 : 2;
 
-  // upload a canonical operand block rows [r0, r1) as a tight device matrix; returns its strides
+  // upload rows [r0, r1) of a canonical operand as a tight device matrix; returns its strides
   auto upload_rows = [&](const float* src, int64_t s_r, int64_t s_k, int64_t r0, int64_t r1, float* dst,
                          int64_t* d_sr, int64_t* d_sk, cudaStream_t s) -> int {
     const int64_t rows = r1 - r0;
@@ -820,24 +822,18 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     return copy2d(ctx, dst, (size_t)rows * 4, src + r0, (size_t)s_k * 4, (size_t)rows * 4, (size_t)K, H2D, s);
   };
 
-  // Q: resident
+  // ---- buffers ----
   float* qraw = nullptr;
-  float* qplanes = nullptr;
-  int64_t q_sr = 1, q_sk = 1;
+  float* q_hi = nullptr;
+  float* q_lo = nullptr;
   BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)cn.No * std::max<int64_t>(K, 1), &qraw));
-  BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, 0, cn.No, qraw, &q_sr, &q_sk, ctx->h2d));
-  cudaEvent_t evQ = get_event(ctx, 0);
-  BOF_CUDA(ctx, cudaEventRecord(evQ, ctx->h2d));
-  BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evQ, 0));
   const size_t qb = plane_bytes(cn.No, kp);
   if (tensor) {
     void* p;
     BOF_TRY(slot_reserve(ctx, S_DENSE_T, 2 * qb, &p));
-    qplanes = static_cast<float*>(p);
-    BOF_TRY(launch_split_planes(ctx, ctx->compute, cn.No, K, qraw, q_sr, q_sk, qplanes,
-                                reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(qplanes) + qb), kp));
+    q_hi = static_cast<float*>(p);
+    q_lo = reinterpret_cast<float*>(static_cast<uint8_t*>(p) + qb);
   }
-
   int64_t rb = (int64_t)ctx->cfg.gemm_row_block;
   rb = std::max<int64_t>(256, round_up<int64_t>(rb, 256));
   rb = std::min(rb, round_up<int64_t>(cn.Mo, 256));
@@ -849,39 +845,53 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     if (tensor) { void* p; BOF_TRY(slot_reserve(ctx, S_PPLANES + g, 2 * pb, &p)); pplanes[g] = static_cast<float*>(p); }
     BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)rb * cn.No, &cblk[g]));
   }
+  auto p_hi_of = [&](int g) { return pplanes[g]; };
+  auto p_lo_of = [&](int g) { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pplanes[g]) + pb); };
+
+  // events: 4+g P block uploaded, 6+g P block split, 8+g block computed, 10+g block downloaded, 16+j Q panel
   bool used[2] = {false, false};
-  // same software-pipelined order as bof_host_csrmm: stage block i+1, then fetch block i
-  auto stage_block = [&](int i) -> int {
+  int64_t q_sr = 1, q_sk = 1;  // strides of the raw Q copy on the device
+
+  auto upload_block = [&](int i) -> int {  // P rows (+ old C rows when beta != 0) of block i
     const int g = i & 1;
     const int64_t r0 = (int64_t)i * rb, r1 = std::min(cn.Mo, r0 + rb), rows = r1 - r0;
-    cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_split = get_event(ctx, 6 + g), ev_done = get_event(ctx, 8 + g),
-                ev_down = get_event(ctx, 10 + g);
     if (used[g]) {
-      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, tensor ? ev_split : ev_done, 0));  // raw P of block i-2 consumed
-      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_down, 0));     // C block buffer free
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, (tensor ? 6 : 8) + g), 0));  // raw P of block i-2 consumed
+      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, 10 + g), 0));  // C buffer free
     }
     int64_t p_sr, p_sk;
     BOF_TRY(upload_rows(cn.psrc, cn.p_sr, cn.p_sk, r0, r1, praw[g], &p_sr, &p_sk, ctx->h2d));
     if (beta != 0.f)
       BOF_TRY(copy2d(ctx, cblk[g], (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
-    BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_up, 0));
-    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_down, 0));
-    if (tensor) {
-      float* p_hi = pplanes[g];
-      float* p_lo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pplanes[g]) + pb);
-      BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi, p_lo, kp));
-      BOF_CUDA(ctx, cudaEventRecord(ev_split, ctx->compute));
-      GemmEpilogue ep;
-      ep.alpha = alpha; ep.beta = beta; ep.C = cblk[g]; ep.ldc = cn.No;
-      BOF_TRY(launch_gemm_tc(ctx, ctx->compute, path == 1 ? 1 : 2, rows, cn.No, K, kp, p_hi, p_lo, qplanes,
-                             reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(qplanes) + qb), ep, k_chunk_of(ctx)));
-    } else {
-      BOF_TRY(launch_gemm_ffma(ctx, ctx->compute, rows, cn.No, K, alpha, praw[g], p_sr, p_sk, qraw, q_sk, q_sr, beta,
-                               cblk[g], cn.No));
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 4 + g), ctx->h2d));
+    return BOF_OK;
+  };
+  // compute of block i against Q rows [n0, n1) (the whole Q when not panelled); `first`/`last` bracket the block
+  auto compute_block = [&](int i, int64_t n0, int64_t n1, bool first, bool last) -> int {
+    const int g = i & 1;
+    const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
+    const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;
+    if (first) {
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 4 + g), 0));
+      if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 10 + g), 0));
+      if (tensor) {
+        BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi_of(g), p_lo_of(g), kp));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 6 + g), ctx->compute));
+      }
     }
-    BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
-    used[g] = true;
+    if (tensor) {
+      GemmEpilogue ep;
+      ep.alpha = alpha; ep.beta = beta; ep.C = cblk[g] + n0; ep.ldc = cn.No;
+      BOF_TRY(launch_gemm_tc(ctx, ctx->compute, cg, rows, n1 - n0, K, kp, p_hi_of(g), p_lo_of(g), q_hi + n0 * kp,
+                             q_lo + n0 * kp, ep, k_chunk_of(ctx)));
+    } else {
+      BOF_TRY(launch_gemm_ffma(ctx, ctx->compute, rows, n1 - n0, K, alpha, praw[g], p_sr, p_sk, qraw + n0 * q_sr, q_sk, q_sr,
+                               beta, cblk[g] + n0, cn.No));
+    }
+    if (last) {
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->compute));
+      used[g] = true;
+    }
     return BOF_OK;
   };
   auto fetch_block = [&](int i) -> int {
@@ -892,9 +902,48 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 10 + g), ctx->d2h));
     return BOF_OK;
   };
-  if (nblk > 0) BOF_TRY(stage_block(0));
+
+  // ---- Q (resident) and block 0 ----
+  // When Q is K-major in the source its rows upload as contiguous panels: panel 0, then P block 0, then the
+  // remaining panels; block 0 is computed panel by panel as they land, so only one panel and one P block of
+  // PCIe time are exposed before the tensor cores start.
+  const bool q_panels = tensor && cn.q_sk == 1 && (size_t)cn.No * K * 4 >= (256u << 20);
+  const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, 8), 256)) : cn.No;
+  const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
+  constexpr int EV_QPAN = 16;
+  auto upload_q_panel = [&](int j) -> int {
+    const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
+    if (q_panels) {
+      q_sr = K; q_sk = 1;
+      BOF_TRY(copy2d(ctx, qraw + n0 * K, (size_t)K * 4, cn.qsrc + n0 * cn.q_sr, (size_t)cn.q_sr * 4, (size_t)K * 4,
+                     (size_t)(n1 - n0), H2D, ctx->h2d));
+    } else {
+      BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, 0, cn.No, qraw, &q_sr, &q_sk, ctx->h2d));
+    }
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->h2d));
+    return BOF_OK;
+  };
+  auto split_q_panel = [&](int j) -> int {
+    const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_QPAN + j), 0));
+    if (!tensor) return BOF_OK;
+    if (q_panels) return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, K, 1, q_hi + n0 * kp, q_lo + n0 * kp, kp);
+    return launch_split_planes(ctx, ctx->compute, cn.No, K, qraw, q_sr, q_sk, q_hi, q_lo, kp);
+  };
+  BOF_TRY(upload_q_panel(0));
+  BOF_TRY(upload_block(0));
+  for (int j = 1; j < n_qpan; ++j) BOF_TRY(upload_q_panel(j));
+  for (int j = 0; j < n_qpan; ++j) {
+    BOF_TRY(split_q_panel(j));
+    const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
+    BOF_TRY(compute_block(0, n0, n1, j == 0, j == n_qpan - 1));
+  }
+  // ---- remaining blocks: stage block i+1 (upload + launch) before fetching block i ----
   for (int i = 0; i < nblk; ++i) {
-    if (i + 1 < nblk) BOF_TRY(stage_block(i + 1));
+    if (i + 1 < nblk) {
+      BOF_TRY(upload_block(i + 1));
+      BOF_TRY(compute_block(i + 1, 0, cn.No, true, true));
+    }
     BOF_TRY(fetch_block(i));
   }
   BOF_TRY(sync_all(ctx));

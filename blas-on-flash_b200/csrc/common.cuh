@@ -59,6 +59,8 @@ struct bof_ctx {
   // CUDA-event bracket of the most recent tensor-core GEMM kernel (for the roofline figure)
   cudaEvent_t tk0 = nullptr, tk1 = nullptr;
   bool tk_valid = false;
+  uint32_t* sync_ctr = nullptr;   // wave lock-step counters of the GEMM kernel
+  size_t sync_ctr_count = 0;
 };
 
 namespace bof {

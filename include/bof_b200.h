@@ -57,6 +57,9 @@ typedef struct bof_config {
   int32_t gemm_k_chunk;      /* k-extent accumulated inside the tensor core before the fp32
                                 round-to-nearest fold (0 = default 256; <0 = whole k)           */
   int32_t gemm_force_path;   /* 0 auto, 1 tcgen05 1-CTA, 2 tcgen05 2-CTA, 3 CUDA-core FFMA      */
+  int32_t gemm_wave_sync;    /* k-blocks (of 32) between wave lock-step points of the GEMM
+                                kernel: 0 = default 64, <0 = off                                */
+  int32_t reserved0;
 } bof_config;
 
 /* Per-stage accounting of the last host entry point, for the out-of-core roofline

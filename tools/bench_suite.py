@@ -221,6 +221,20 @@ def gemm_chunk_sweep(bof, sizes=(32768,), chunks=(128, 256, 512, 1024)):
     return out
 
 
+def gemm_sync_sweep(bof, n=32768, syncs=(-1, 16, 64, 256)):
+    """A/B of the wave lock-step (bof_config.gemm_wave_sync) on the headline shape."""
+    out = []
+    A = torch.rand((n, n), device="cuda"); B = torch.rand((n, n), device="cuda"); Cm = torch.empty((n, n), device="cuda")
+    for sy in syncs:
+        with bof.Context(device=0, gemm_wave_sync=sy) as c2:
+            ws = c2.sgemm_workspace(n, n, n)
+            t, tmin = time_gpu(lambda: c2.sgemm("R", "N", "N", n, n, n, 1.0, A, 0, B, 0, 0.0, Cm, 0, ws=ws), iters=3, warm=2)
+            out.append({"config": f"gemm {n}^3 wave_sync={sy}", "ms": t * 1e3, "ms_min": tmin * 1e3, "kernel_ms": c2.stats().kernel_ms,
+                        "tflops": 2.0 * n ** 3 / t / 1e12})
+            del ws
+    return out
+
+
 def tf32_cublas_peak():
     """Denominator only: cuBLAS TF32 GEMM (library call, not on the product path)."""
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -276,6 +290,8 @@ def main():
         add(spmm_record(ctx, "cfg1 csrmm 262144^2, 64 nnz/row, k=128", 262144, 262144, 64, 128, flush))
     if "chunks" in only:
         add(gemm_chunk_sweep(bof))
+    if "sync" in only:
+        add(gemm_sync_sweep(bof))
     big = int((1 << 23) * args.scale)
     if "cfg3" in only:
         add(spmm_record(ctx, f"cfg3 csrmm {big}^2, 100 nnz/row, k=256", big, big, 100, 256, None, seed=3))

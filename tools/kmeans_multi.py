@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""cfg-5 under torchrun: points sharded over the ranks and resident, per iteration one NCCL allreduce of
+[K*d sums | K counts] on the library's stream (the only collective on the path).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/kmeans_multi.py [--points 10000000] [--iters 20] [--check]
+
+--check additionally runs a small problem on every rank's full copy with world size 1 semantics (rank 0
+alone, no allreduce) and verifies that the sharded run produces the same assignments and centroids.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import __graft_entry__ as g  # noqa: E402
+
+
+def make_points(P, K, d, seed, device):
+    gen = torch.Generator(device=device); gen.manual_seed(seed)
+    cent = torch.randn((K, d), device=device, generator=gen) * 4
+    lab = torch.randint(0, K, (P,), device=device, generator=gen)
+    return (cent[lab] + 0.5 * torch.randn((P, d), device=device, generator=gen)), cent
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=10_000_000)
+    ap.add_argument("--centers", type=int, default=1024)
+    ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bof = g.load_package()
+    from bof_b200 import dist as bdist
+    ctx = bof.Context(device=local)
+    dev = f"cuda:{local}"
+    out = {"world": world}
+
+    if args.check:
+        P, K, d = 200_000, 64, 32
+        pts, _ = make_points(P, K, d, 1, dev)  # same seed on every rank -> identical data
+        pts_h = pts.cpu().numpy(); c0 = pts_h[:K].copy()
+        p0, p1 = bdist.row_shard(P, world, rank)
+        km = bof.KMeans(ctx, p1 - p0, K, d, pts_h[p0:p1], c0)
+        bdist.lloyd(km, 5)
+        cs = np.zeros((K, d), np.float32); a_s = np.zeros(p1 - p0, np.int64)
+        km.get(cs, a_s); km.close()
+        km1 = bof.KMeans(ctx, P, K, d, pts_h, c0)  # unsharded replica, no collective
+        for _ in range(5):
+            km1.local_step(); km1.update()
+        c1 = np.zeros((K, d), np.float32); a1 = np.zeros(P, np.int64)
+        km1.get(c1, a1); km1.close()
+        rel = float(np.linalg.norm(cs - c1) / np.linalg.norm(c1))
+        mism = int((a_s != a1[p0:p1]).sum())
+        t = torch.tensor([rel, float(mism)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["check"] = {"centroid_rel_err_vs_unsharded": float(t[0]), "assignment_mismatches_max_rank": int(t[1])}
+        assert float(t[0]) <= 1e-5, out
+
+    P, K, d = args.points, args.centers, args.dim
+    p0, p1 = bdist.row_shard(P, world, rank)
+    n_loc = p1 - p0
+    pts_h = torch.empty((n_loc, d), dtype=torch.float32, pin_memory=True)
+    cent_true = make_points(1, K, d, 7, dev)[1]
+    gen = torch.Generator(device=dev); gen.manual_seed(100 + rank)
+    for r0 in range(0, n_loc, 1 << 20):
+        r1 = min(n_loc, r0 + (1 << 20))
+        lab = torch.randint(0, K, (r1 - r0,), device=dev, generator=gen)
+        pts_h[r0:r1].copy_(cent_true[lab] + 0.5 * torch.randn((r1 - r0, d), device=dev, generator=gen))
+    c0 = torch.empty((K, d), dtype=torch.float32)
+    if rank == 0:
+        c0.copy_(pts_h[:K])
+    if world > 1:
+        c0d = c0.to(dev); dist.broadcast(c0d, 0); c0 = c0d.cpu()
+    km = bof.KMeans(ctx, n_loc, K, d, pts_h, c0)
+    bdist.lloyd(km, 2)  # warm-up (NCCL channels, clocks)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(km.stream(), device=local)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(stream)
+    bdist.lloyd(km, args.iters)
+    e1.record(stream)
+    stream.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cent = np.zeros((K, d), np.float32)
+    km.get(cent, None); km.close()
+    secs = float(t[0])
+    out.update({"config": f"cfg5 kmeans {P}x{d}, k={K}, {args.iters} iterations, {world} GPU(s), points sharded + resident",
+                "s_total": secs, "ms_per_iter": secs / args.iters * 1e3,
+                "distance_tflops_job": 2.0 * P * K * d * args.iters / secs / 1e12,
+                "collective": "NCCL all_reduce(SUM) of K*d+K fp32 per iteration" if world > 1 else "none (1 GPU)",
+                "centers_checksum": float(np.abs(cent).sum())})
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
