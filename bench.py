@@ -37,7 +37,7 @@ sys.path.insert(0, str(ROOT))
 M_FULL = N_FULL = K_FULL = 32768
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size gemm3xtf32_kernel launch, from the
 # ncu --set full capture summarised in profiles/ (None until that capture exists)
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 275563161856 + 4640736768  # profiles/r01/ncu_gemm32k_sync.csv (trip 5)
 TILE = 8192  # reference GEMM_BLK_SIZE (CMakeLists.txt:46-50 of the reference)
 
 

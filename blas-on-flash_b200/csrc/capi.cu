@@ -930,17 +930,31 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     if (q_panels) return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, K, 1, q_hi + n0 * kp, q_lo + n0 * kp, kp);
     return launch_split_planes(ctx, ctx->compute, cn.No, K, qraw, q_sr, q_sk, q_hi, q_lo, kp);
   };
+  // Prologue: the first two P blocks ride between the Q panels (h2d order Q0 P0 Q1 P1 Q2 .. Qn) and are
+  // computed against each panel as it lands (compute order follows the arrival order), so the tensor
+  // cores start after one panel + one block of PCIe time and stay fed while the rest of Q uploads.
+  const int npro = std::min(nblk, n_qpan > 1 ? 2 : 1);  // blocks handled by the prologue
+  auto pan = [&](int j, int64_t* n0, int64_t* n1) { *n0 = (int64_t)j * qpan_rows; *n1 = std::min(cn.No, *n0 + qpan_rows); };
   BOF_TRY(upload_q_panel(0));
   BOF_TRY(upload_block(0));
-  for (int j = 1; j < n_qpan; ++j) BOF_TRY(upload_q_panel(j));
+  if (n_qpan > 1) BOF_TRY(upload_q_panel(1));
+  if (npro > 1) BOF_TRY(upload_block(1));
+  for (int j = 2; j < n_qpan; ++j) BOF_TRY(upload_q_panel(j));
   for (int j = 0; j < n_qpan; ++j) {
+    int64_t n0, n1;
+    pan(j, &n0, &n1);
     BOF_TRY(split_q_panel(j));
-    const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
-    BOF_TRY(compute_block(0, n0, n1, j == 0, j == n_qpan - 1));
+    const bool last = j == n_qpan - 1;
+    BOF_TRY(compute_block(0, n0, n1, j == 0, last));
+    if (npro > 1 && j >= 1) {
+      // block 1 arrived after panel 1: panels 0..1 in one launch, later panels one by one
+      if (j == 1) BOF_TRY(compute_block(1, 0, n1, true, last));
+      else BOF_TRY(compute_block(1, n0, n1, false, last));
+    }
   }
-  // ---- remaining blocks: stage block i+1 (upload + launch) before fetching block i ----
+  // ---- steady state: stage block i+1 (upload + launch) before fetching block i ----
   for (int i = 0; i < nblk; ++i) {
-    if (i + 1 < nblk) {
+    if (i + 1 < nblk && i + 1 >= npro) {
       BOF_TRY(upload_block(i + 1));
       BOF_TRY(compute_block(i + 1, 0, cn.No, true, true));
     }
