@@ -33,6 +33,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread (must be set before
+    # libgomp / MKL initialise, i.e. before numpy or torch are imported)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 M_FULL = N_FULL = K_FULL = 32768
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size gemm3xtf32_kernel launch, from the

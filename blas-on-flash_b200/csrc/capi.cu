@@ -907,19 +907,17 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
   // When Q is K-major in the source its rows upload as contiguous panels: panel 0, then P block 0, then the
   // remaining panels; block 0 is computed panel by panel as they land, so only one panel and one P block of
   // PCIe time are exposed before the tensor cores start.
-  const bool q_panels = tensor && cn.q_sk == 1 && (size_t)cn.No * K * 4 >= (256u << 20);
+  const bool q_panels = tensor && (size_t)cn.No * K * 4 >= (256u << 20);
   const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, 8), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
   constexpr int EV_QPAN = 16;
+  // Every panel is kept as its own tight block at qraw + n0*K: [rows x K] when Q is K-major in the source,
+  // [K x rows] (a column range of the stored matrix, pitched copy) when it is not.
+  std::vector<int64_t> pan_sr((size_t)n_qpan, 1), pan_sk((size_t)n_qpan, 1);
   auto upload_q_panel = [&](int j) -> int {
     const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
-    if (q_panels) {
-      q_sr = K; q_sk = 1;
-      BOF_TRY(copy2d(ctx, qraw + n0 * K, (size_t)K * 4, cn.qsrc + n0 * cn.q_sr, (size_t)cn.q_sr * 4, (size_t)K * 4,
-                     (size_t)(n1 - n0), H2D, ctx->h2d));
-    } else {
-      BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, 0, cn.No, qraw, &q_sr, &q_sk, ctx->h2d));
-    }
+    BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &pan_sr[j], &pan_sk[j], ctx->h2d));
+    if (n_qpan == 1) { q_sr = pan_sr[0]; q_sk = pan_sk[0]; }
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->h2d));
     return BOF_OK;
   };
@@ -927,8 +925,8 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
     const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_QPAN + j), 0));
     if (!tensor) return BOF_OK;
-    if (q_panels) return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, K, 1, q_hi + n0 * kp, q_lo + n0 * kp, kp);
-    return launch_split_planes(ctx, ctx->compute, cn.No, K, qraw, q_sr, q_sk, q_hi, q_lo, kp);
+    return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, pan_sr[j], pan_sk[j], q_hi + n0 * kp,
+                               q_lo + n0 * kp, kp);
   };
   // Prologue: the first two P blocks ride between the Q panels (h2d order Q0 P0 Q1 P1 Q2 .. Qn) and are
   // computed against each panel as it lands (compute order follows the arrival order), so the tensor

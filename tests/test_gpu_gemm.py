@@ -128,6 +128,22 @@ def test_gemm_long_k_accuracy(bof, k_chunk):
         assert err <= TOL, err
 
 
+def test_gemm_wave_lockstep_is_result_neutral(bof):
+    """The wave lock-step only paces the TMA producers: results are bit-identical with it on, off, or dense."""
+    M, N, K = 2560, 2816, 8192  # 10 x 11 = 110 tiles > 74 clusters, 256 k-blocks
+    A = oracle.gen_dense((M, K), seed=41)
+    B = oracle.gen_dense((K, N), seed=42)
+    outs = []
+    for sync in (-1, 0, 8):
+        with bof.Context(device=0, gemm_wave_sync=sync) as c2:
+            Cd = torch.empty((M, N), device="cuda")
+            c2.sgemm("R", "N", "N", M, N, K, 1.0, dev(A), 0, dev(B), 0, 0.0, Cd, 0)
+            outs.append(Cd.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = A[:64].astype(np.float64) @ B.astype(np.float64)
+    assert oracle.rel_fro(outs[1][:64].numpy(), ref) <= TOL
+
+
 def test_gemm_linearity_full_size_property(ctx):
     """Size-independent check at 8192^2 x 4096: (A1 + A2) B == A1 B + A2 B with integer-valued data (exact)."""
     M, N, K = 8192, 8192, 4096

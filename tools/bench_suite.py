@@ -235,6 +235,30 @@ def gemm_sync_sweep(bof, n=32768, syncs=(-1, 16, 64, 256)):
     return out
 
 
+def pcie_record():
+    """Out-of-core roofline denominators: pinned cudaMemcpyAsync H2D, D2H, and both at once (1 GiB each)."""
+    n = 1 << 28
+    h_in = torch.empty(n, dtype=torch.float32, pin_memory=True); h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty(n, dtype=torch.float32, device="cuda"); d_out = torch.rand(n, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {}
+    for name in ("h2d", "d2h", "both"):
+        best = 1e9
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if name in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if name in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        res[name + "_gbs"] = (2 if name == "both" else 1) * n * 4 / best / 1e9
+    return {"config": "PCIe pinned copy bandwidth (1 GiB transfers)", **res}
+
+
 def tf32_cublas_peak():
     """Denominator only: cuBLAS TF32 GEMM (library call, not on the product path)."""
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -286,6 +310,8 @@ def main():
 
     if "tf32" in only:
         add(tf32_cublas_peak())
+    if "pcie" in only:
+        add(pcie_record())
     if "cfg1" in only:
         add(spmm_record(ctx, "cfg1 csrmm 262144^2, 64 nnz/row, k=128", 262144, 262144, 64, 128, flush))
     if "chunks" in only:
