@@ -50,26 +50,34 @@ def main():
     out = {"world": world}
 
     if args.check:
+        # One iteration from identical centers must agree exactly in assignments and to rounding in centroids
+        # (only the order of the cross-rank sum differs).  Over several iterations the trajectories may drift:
+        # a 1e-7 centroid difference can flip a near-tie point later on ("kmeans parity
+        # across iterations"), so the multi-iteration comparison is reported and only loosely bounded.
         P, K, d = 200_000, 64, 32
         pts, _ = make_points(P, K, d, 1, dev)  # same seed on every rank -> identical data
         pts_h = pts.cpu().numpy(); c0 = pts_h[:K].copy()
         p0, p1 = bdist.row_shard(P, world, rank)
-        km = bof.KMeans(ctx, p1 - p0, K, d, pts_h[p0:p1], c0)
-        bdist.lloyd(km, 5)
-        cs = np.zeros((K, d), np.float32); a_s = np.zeros(p1 - p0, np.int64)
-        km.get(cs, a_s); km.close()
-        km1 = bof.KMeans(ctx, P, K, d, pts_h, c0)  # unsharded replica, no collective
-        for _ in range(5):
-            km1.local_step(); km1.update()
-        c1 = np.zeros((K, d), np.float32); a1 = np.zeros(P, np.int64)
-        km1.get(c1, a1); km1.close()
-        rel = float(np.linalg.norm(cs - c1) / np.linalg.norm(c1))
-        mism = int((a_s != a1[p0:p1]).sum())
-        t = torch.tensor([rel, float(mism)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out["check"] = {"centroid_rel_err_vs_unsharded": float(t[0]), "assignment_mismatches_max_rank": int(t[1])}
-        assert float(t[0]) <= 1e-5, out
+        res = {}
+        for iters in (1, 5):
+            km = bof.KMeans(ctx, p1 - p0, K, d, pts_h[p0:p1], c0)
+            bdist.lloyd(km, iters)
+            cs = np.zeros((K, d), np.float32); a_s = np.zeros(p1 - p0, np.int64)
+            km.get(cs, a_s); km.close()
+            km1 = bof.KMeans(ctx, P, K, d, pts_h, c0)  # unsharded replica, no collective
+            for _ in range(iters):
+                km1.local_step(); km1.update()
+            c1 = np.zeros((K, d), np.float32); a1 = np.zeros(P, np.int64)
+            km1.get(c1, a1); km1.close()
+            rel = float(np.linalg.norm(cs - c1) / np.linalg.norm(c1))
+            mism = int((a_s != a1[p0:p1]).sum())
+            t = torch.tensor([rel, float(mism)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[f"iters_{iters}"] = {"centroid_rel_err_vs_unsharded": float(t[0]), "assignment_mismatches_max_rank": int(t[1])}
+        out["check"] = res
+        assert res["iters_1"]["centroid_rel_err_vs_unsharded"] <= 1e-5 and res["iters_1"]["assignment_mismatches_max_rank"] == 0, out
+        assert res["iters_5"]["assignment_mismatches_max_rank"] <= P // 1000, out
 
     P, K, d = args.points, args.centers, args.dim
     p0, p1 = bdist.row_shard(P, world, rank)
