@@ -27,7 +27,7 @@ class BofConfig(C.Structure):
         ("gemm_k_chunk", C.c_int32),
         ("gemm_force_path", C.c_int32),
         ("gemm_wave_sync", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("gemm_split", C.c_int32),
     ]
 
 

@@ -24,6 +24,12 @@
 //            bounds the error of the tensor core's internal accumulation for very long k.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
+#ifndef BOF_DEFAULT_HYBRID
+#define BOF_DEFAULT_HYBRID 0
+#endif
+
 namespace bof {
 namespace tc {
 
@@ -180,6 +186,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
   }
 }
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 operands selected by the instruction descriptor)
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // Arrive on `bar` (same offset in every CTA of the pair) once all previously issued MMAs retire.
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -222,10 +246,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // layout: SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
+// fp32 accumulate, both operands K-major; fmt: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16)
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, uint32_t fmt = 2u) {
   return (1u << 4)                      // c_format = F32
-         | (2u << 7) | (2u << 10)       // a_format = b_format = TF32
+         | (fmt << 7) | (fmt << 10)     // a_format = b_format
          | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
@@ -254,7 +278,7 @@ constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail) + 
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <int CG, int EPI, bool CHUNKED>
+template <int CG, int EPI, bool CHUNKED, bool HYB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_constant__ CUtensorMap map_p_lo,
                   const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
@@ -263,7 +287,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
   constexpr int TILE_M = BLOCK_M * CG;
   constexpr int EPI_COLS = BLOCK_N / 2;  // columns per epilogue thread
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
-  constexpr uint32_t IDESC = make_idesc(BLOCK_M * CG, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc(BLOCK_M * CG, BLOCK_N, 2u);
+  constexpr uint32_t IDESC_BF16 = make_idesc(BLOCK_M * CG, BLOCK_N, 1u);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -380,13 +405,29 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
                 const uint64_t d_p_lo = make_smem_desc(st + PLANE_BYTES);
                 const uint64_t d_q_hi = make_smem_desc(st + 2 * PLANE_BYTES);
                 const uint64_t d_q_lo = make_smem_desc(st + 3 * PLANE_BYTES);
+                const uint32_t fresh = (kb == c * prm.kb_per_chunk) ? 0u : 1u;  // first MMA of a chunk overwrites
+                if constexpr (HYB) {
+                  // Second plane = bf16 pairs per 32-k group: bytes [0,64) bf16(hi), [64,128) bf16(lo).
+                  // Cross terms on the bf16 pipe (K = 16 per MMA = 32 B), hi*hi on the tf32 pipe.
 #pragma unroll
-                for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                  const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // 32 B per k-step
-                  const uint32_t first = (kb == c * prm.kb_per_chunk && kk == 0) ? 0u : 1u;
-                  umma_tf32<CG>(tmem_d, d_p_lo + adv, d_q_hi + adv, IDESC, first);
-                  umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_lo + adv, IDESC, 1u);
-                  umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_hi + adv, IDESC, 1u);
+                  for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);                  // 32 B per k-step of 16 bf16
+                    umma_bf16<CG>(tmem_d, d_p_lo + 4 + adv, d_q_lo + adv, IDESC_BF16, kk == 0 ? fresh : 1u);  // lo * hi
+                    umma_bf16<CG>(tmem_d, d_p_lo + adv, d_q_lo + 4 + adv, IDESC_BF16, 1u);                    // hi * lo
+                  }
+#pragma unroll
+                  for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
+                    umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_hi + adv, IDESC, 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);  // 32 B per k-step
+                    umma_tf32<CG>(tmem_d, d_p_lo + adv, d_q_hi + adv, IDESC, kk == 0 ? fresh : 1u);
+                    umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_lo + adv, IDESC, 1u);
+                    umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_hi + adv, IDESC, 1u);
+                  }
                 }
                 umma_commit<CG>(&tail->empty[stage]);  // frees the stage in both CTAs
                 if (kb == kb_end - 1) umma_commit<CG>(&tail->tmem_full[buf]);
@@ -542,11 +583,18 @@ __device__ __forceinline__ void split1(float x, float& hi, float& lo) {
   hi = rna_tf32(x);
   lo = rna_tf32(x - hi);
 }
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+// Hybrid second plane: per 32-element k group (128 bytes) 32 x bf16(hi) then 32 x bf16(lo), lo = x - hi exact.
+__device__ __forceinline__ uint8_t* combo_ptr(float* plane, int64_t r, int64_t kp, int64_t kk, bool lo_half) {
+  return reinterpret_cast<uint8_t*>(plane + r * kp) + (kk >> 5) * 128 + (lo_half ? 64 : 0) + (kk & 31) * 2;
+}
 
 // K contiguous in the source (s_k == 1): element-wise, 4 k-elements per thread.
 __global__ void __launch_bounds__(256)
 split_planes_kmajor_kernel(int64_t R, int64_t K, const float* __restrict__ src, int64_t s_r,
-                           float* __restrict__ hi, float* __restrict__ lo, int64_t kp, bool vec) {
+                           float* __restrict__ hi, float* __restrict__ lo, int64_t kp, bool vec, bool combo) {
   const int64_t quads_per_row = kp / 4;
   const int64_t total = R * quads_per_row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -568,7 +616,18 @@ split_planes_kmajor_kernel(int64_t R, int64_t K, const float* __restrict__ src, 
     split1(x[2], h.z, l.z);
     split1(x[3], h.w, l.w);
     *reinterpret_cast<float4*>(hi + r * kp + k0) = h;
-    *reinterpret_cast<float4*>(lo + r * kp + k0) = l;
+    if (!combo) {
+      *reinterpret_cast<float4*>(lo + r * kp + k0) = l;
+    } else {
+      const float e[4] = {x[0] - h.x, x[1] - h.y, x[2] - h.z, x[3] - h.w};  // exact in fp32
+      uint2 ph, pl;
+      ph.x = bf16_bits(h.x) | ((uint32_t)bf16_bits(h.y) << 16);
+      ph.y = bf16_bits(h.z) | ((uint32_t)bf16_bits(h.w) << 16);
+      pl.x = bf16_bits(e[0]) | ((uint32_t)bf16_bits(e[1]) << 16);
+      pl.y = bf16_bits(e[2]) | ((uint32_t)bf16_bits(e[3]) << 16);
+      *reinterpret_cast<uint2*>(combo_ptr(lo, r, kp, k0, false)) = ph;
+      *reinterpret_cast<uint2*>(combo_ptr(lo, r, kp, k0, true)) = pl;
+    }
   }
 }
 
@@ -576,7 +635,7 @@ split_planes_kmajor_kernel(int64_t R, int64_t K, const float* __restrict__ src, 
 __global__ void __launch_bounds__(256)
 split_planes_transpose_kernel(int64_t R, int64_t K, const float* __restrict__ src, int64_t s_k,
                               float* __restrict__ hi, float* __restrict__ lo, int64_t kp,
-                              unsigned tiles_k) {
+                              unsigned tiles_k, bool combo) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)(blockIdx.x / tiles_k) * 32, k0 = (int64_t)(blockIdx.x % tiles_k) * 32;
@@ -591,9 +650,15 @@ split_planes_transpose_kernel(int64_t R, int64_t K, const float* __restrict__ sr
     const int64_t r = r0 + i, kk = k0 + tx;
     if (r < R && kk < kp) {
       float h, l;
-      split1(tile[tx][i], h, l);
+      const float x = tile[tx][i];
+      split1(x, h, l);
       hi[r * kp + kk] = h;
-      lo[r * kp + kk] = l;
+      if (!combo) {
+        lo[r * kp + kk] = l;
+      } else {
+        *reinterpret_cast<uint16_t*>(combo_ptr(lo, r, kp, kk, false)) = bf16_bits(h);
+        *reinterpret_cast<uint16_t*>(combo_ptr(lo, r, kp, kk, true)) = bf16_bits(x - h);
+      }
     }
   }
 }
@@ -652,6 +717,9 @@ gemm_ffma_kernel(int64_t M, int64_t N, int64_t K, float alpha, const float* __re
   }
 }
 
+// bof_config.gemm_split: 1 = pure 3xTF32; 2 = hybrid (TF32 hi*hi + two BF16 cross terms); 0 = default
+bool hybrid_split(const bof_ctx* ctx) { return ctx->cfg.gemm_split == 2 || (ctx->cfg.gemm_split == 0 && BOF_DEFAULT_HYBRID); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -671,9 +739,9 @@ int make_plane_map(bof_ctx* ctx, CUtensorMap* map, const float* plane, int64_t r
   return BOF_OK;
 }
 
-template <int CG, int EPI, bool CHUNKED>
+template <int CG, int EPI, bool CHUNKED, bool HYB>
 int launch_variant(bof_ctx* ctx, cudaStream_t s, const CUtensorMap* maps, const tc::Params& prm, int num_items) {
-  auto kern = tc::gemm3xtf32_kernel<CG, EPI, CHUNKED>;
+  auto kern = tc::gemm3xtf32_kernel<CG, EPI, CHUNKED, HYB>;
   static bool attr_set = false;
   if (!attr_set) {
     BOF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
@@ -715,14 +783,14 @@ int launch_split_planes(bof_ctx* ctx, cudaStream_t s, int64_t R, int64_t K, cons
     const bool vec = (s_r % 4 == 0) && aligned16(src);
     const int64_t total = R * (kp / 4);
     const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(total, 256), (int64_t)ctx->num_sms * 32);
-    split_planes_kmajor_kernel<<<grid, 256, 0, s>>>(R, K, src, s_r, hi, lo, kp, vec);
+    split_planes_kmajor_kernel<<<grid, 256, 0, s>>>(R, K, src, s_r, hi, lo, kp, vec, hybrid_split(ctx));
     BOF_LAUNCH_CHECK(ctx, "split_planes_kmajor_kernel");
   } else {
     BOF_REQUIRE(ctx, s_r == 1, "split: one of the operand strides must be 1");
     const int64_t tiles_k = kp / 32, tiles_r = ceil_div<int64_t>(R, 32);
     BOF_REQUIRE(ctx, tiles_k * tiles_r < (1ll << 31), "split: operand too large for one launch");
     split_planes_transpose_kernel<<<(unsigned)(tiles_k * tiles_r), 256, 0, s>>>(R, K, src, s_k, hi, lo, kp,
-                                                                               (unsigned)tiles_k);
+                                                                               (unsigned)tiles_k, hybrid_split(ctx));
     BOF_LAUNCH_CHECK(ctx, "split_planes_transpose_kernel");
   }
   return BOF_OK;
@@ -785,7 +853,12 @@ int launch_gemm_tc(bof_ctx* ctx, cudaStream_t s, int cta_group, int64_t M, int64
     prm.sync_counters = ctx->sync_ctr;
   }
 
-#define BOF_TC(CG, EPI, CH) return launch_variant<CG, EPI, CH>(ctx, s, maps, prm, num_items)
+  const bool hyb = hybrid_split(ctx);
+#define BOF_TC(CG, EPI, CH)                                                            \
+  do {                                                                                 \
+    if (hyb) return launch_variant<CG, EPI, CH, true>(ctx, s, maps, prm, num_items);   \
+    return launch_variant<CG, EPI, CH, false>(ctx, s, maps, prm, num_items);           \
+  } while (0)
   if (cta_group == 2) {
     if (argmin) { if (chunked) BOF_TC(2, tc::EPI_ARGMIN, true); else BOF_TC(2, tc::EPI_ARGMIN, false); }
     if (chunked) BOF_TC(2, tc::EPI_GEMM, true); else BOF_TC(2, tc::EPI_GEMM, false);

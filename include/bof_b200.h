@@ -59,7 +59,10 @@ typedef struct bof_config {
   int32_t gemm_force_path;   /* 0 auto, 1 tcgen05 1-CTA, 2 tcgen05 2-CTA, 3 CUDA-core FFMA      */
   int32_t gemm_wave_sync;    /* k-blocks (of 32) between wave lock-step points of the GEMM
                                 kernel: 0 = default 64, <0 = off                                */
-  int32_t reserved0;
+  int32_t gemm_split;        /* operand split of the fp32 GEMM: 0 = default, 1 = 3xTF32 (lo*hi + hi*lo +
+                                hi*hi, all kind::tf32), 2 = hybrid (hi*hi kind::tf32, the two cross
+                                terms on bf16 copies, kind::f16: 2/3 of the tensor time, cross-term
+                                error <= 2^-19 relative)                                          */
 } bof_config;
 
 /* Per-stage accounting of the last host entry point, for the out-of-core roofline

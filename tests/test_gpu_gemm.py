@@ -12,12 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5  # relative Frobenius error, BASELINE.json north_star
 G = np.load(Path(__file__).parent / "golden" / "golden_small.npz")
 
-PATHS = {"tc1": 1, "tc2": 2, "ffma": 3}
+# name -> (gemm_force_path, gemm_split): tc = pure 3xTF32, hyb = TF32 hi*hi + BF16 cross terms
+PATHS = {"tc1": (1, 1), "tc2": (2, 1), "ffma": (3, 0), "hyb1": (1, 2), "hyb2": (2, 2)}
 
 
 @pytest.fixture(scope="module", params=list(PATHS))
 def pctx(bof, request):
-    c = bof.Context(device=0, gemm_force_path=PATHS[request.param])
+    path, split = PATHS[request.param]
+    c = bof.Context(device=0, gemm_force_path=path, gemm_split=split)
     c.path = request.param
     yield c
     c.close()
@@ -111,20 +113,37 @@ def test_gemm_integer_data_exact(ctx):
     assert np.array_equal(Cd.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("k_chunk", [-1, 512, 2048])
-def test_gemm_long_k_accuracy(bof, k_chunk):
+@pytest.mark.parametrize("split", [1, 2])
+def test_gemm_split_modes_worst_case_data(bof, split):
+    """Constant matrices make every product carry the same rounding error (no cancellation across k): the
+    adversarial case for the bf16 cross terms of the hybrid split (bound 2^-19 per product)."""
+    M, N, K = 512, 512, 4096
+    for va, vb in ((1.2345678, 0.87654321), (1.9999999, 1.0000001), (3.1415927, 2.7182817)):
+        A = np.full((M, K), va, np.float32); B = np.full((K, N), vb, np.float32)
+        ref = A.astype(np.float64) @ B.astype(np.float64)
+        with bof.Context(device=0, gemm_split=split) as c2:
+            Cd = torch.empty((M, N), device="cuda")
+            c2.sgemm("R", "N", "N", M, N, K, 1.0, dev(A), 0, dev(B), 0, 0.0, Cd, 0)
+            err = oracle.rel_fro(Cd.cpu().numpy(), ref)
+        print(f"split={split} constant data ({va}, {vb}): rel-Frobenius {err:.3e}")
+        assert err <= TOL, (split, va, vb, err)
+
+
+@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("k_chunk", [-1, 256, 2048])
+def test_gemm_long_k_accuracy(bof, k_chunk, split):
     """k = 32768 (cfg-2's reduction length) with all-positive data: the worst case for accumulator
     rounding.  Reference = fp64 accumulation."""
     M, N, K = 256, 256, 32768
     A = oracle.gen_dense((M, K), seed=31)
     B = oracle.gen_dense((K, N), seed=32)
     ref = A.astype(np.float64) @ B.astype(np.float64)
-    with bof.Context(device=0, gemm_k_chunk=k_chunk) as c2:
+    with bof.Context(device=0, gemm_k_chunk=k_chunk, gemm_split=split) as c2:
         Cd = torch.empty((M, N), device="cuda")
         c2.sgemm("R", "N", "N", M, N, K, 1.0, dev(A), 0, dev(B), 0, 0.0, Cd, 0)
         err = oracle.rel_fro(Cd.cpu().numpy(), ref)
-    print(f"long-k rel-Frobenius error with k_chunk={k_chunk}: {err:.3e}")
-    if k_chunk == 512:  # the shipped default must hold the tolerance
+    print(f"long-k rel-Frobenius error with k_chunk={k_chunk} split={split}: {err:.3e}")
+    if k_chunk == 256:  # the shipped default must hold the tolerance
         assert err <= TOL, err
 
 

@@ -44,6 +44,17 @@ def test_assign_bit_exact_on_ties_free_points(ctx, P, K, d):
     assert got.min() >= 0 and got.max() < K
 
 
+def test_assign_hybrid_split_mode(bof):
+    """Same bit-exact-on-ties-free contract with the hybrid operand split (gemm_split=2)."""
+    rng = np.random.default_rng(77)
+    pts, cent = mixture(rng, 6000, 512, 128)
+    with bof.Context(device=0, gemm_split=2) as c2:
+        got, p2, _ = gpu_assign(c2, pts, cent)
+    ref, margin = oracle.kmeans_assign(pts, cent)
+    ok = margin > 1e-3 * (1 + np.abs(p2))
+    assert ok.mean() > 0.95 and np.array_equal(got[ok], ref[ok])
+
+
 def test_assign_golden(ctx):
     pts, cent = G["km_points"], G["km_centers"]
     got, _, _ = gpu_assign(ctx, pts, cent)

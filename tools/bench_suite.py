@@ -221,6 +221,23 @@ def gemm_chunk_sweep(bof, sizes=(32768,), chunks=(128, 256, 512, 1024)):
     return out
 
 
+def gemm_split_sweep(bof, n=32768):
+    """Pure 3xTF32 vs hybrid (TF32 + 2 x BF16 cross terms) on the headline shape, with sampled accuracy."""
+    out = []
+    A = torch.rand((n, n), device="cuda"); B = torch.rand((n, n), device="cuda"); Cm = torch.empty((n, n), device="cuda")
+    ii = torch.randint(0, n, (256,), device="cuda"); jj = torch.randint(0, n, (256,), device="cuda")
+    ref = (A[ii].double() * B[:, jj].t().double()).sum(1)
+    for split in (1, 2):
+        with bof.Context(device=0, gemm_split=split) as c2:
+            ws = c2.sgemm_workspace(n, n, n)
+            t, tmin = time_gpu(lambda: c2.sgemm("R", "N", "N", n, n, n, 1.0, A, 0, B, 0, 0.0, Cm, 0, ws=ws), iters=3, warm=2)
+            err = float(((Cm[ii, jj].double() - ref).norm() / ref.norm()))
+            out.append({"config": f"gemm {n}^3 gemm_split={split}", "ms": t * 1e3, "kernel_ms": c2.stats().kernel_ms,
+                        "tflops": 2.0 * n ** 3 / t / 1e12, "sampled_rel_fro_err": err})
+            del ws
+    return out
+
+
 def gemm_sync_sweep(bof, n=32768, syncs=(-1, 16, 64, 256)):
     """A/B of the wave lock-step (bof_config.gemm_wave_sync) on the headline shape."""
     out = []
@@ -318,6 +335,8 @@ def main():
         add(gemm_chunk_sweep(bof))
     if "sync" in only:
         add(gemm_sync_sweep(bof))
+    if "split" in only:
+        add(gemm_split_sweep(bof))
     big = int((1 << 23) * args.scale)
     if "cfg3" in only:
         add(spmm_record(ctx, f"cfg3 csrmm {big}^2, 100 nnz/row, k=256", big, big, 100, 256, None, seed=3))

@@ -21,9 +21,10 @@ if "gemm" in which:
         ctx.sgemm("R", "N", "N", n, n, n, 1.0, A, 0, B, 0, 0.0, C, 0, ws=ws)
     torch.cuda.synchronize()
     del A, B, C, ws
-if "gemm32k" in which or "gemm32k_nosync" in which:
+if "gemm32k" in which or "gemm32k_nosync" in which or "gemm32k_hyb" in which:
     n = 32768
-    c2 = bof.Context(device=0, gemm_wave_sync=-1 if "gemm32k_nosync" in which else 0)
+    c2 = bof.Context(device=0, gemm_wave_sync=-1 if "gemm32k_nosync" in which else 0,
+                     gemm_split=2 if "gemm32k_hyb" in which else 1)
     A = torch.rand((n, n), device="cuda"); B = torch.rand((n, n), device="cuda"); C = torch.empty((n, n), device="cuda")
     ws = c2.sgemm_workspace(n, n, n)
     for _ in range(2):
