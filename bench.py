@@ -9,13 +9,14 @@ alpha 1 beta 0, output row blocks sharded over the N ranks with no collective (s
 the job is fixed, rank r owns C rows [r*M/N, (r+1)*M/N), B is replicated).
 A "step" is one pass of the hot path over that job.
 
-  value   whole-job GFLOP/s with the operands resident in HBM (bof_sgemm_f32: TF32 split of both
-          operands + the tcgen05 kernel), CUDA-event timed, max over ranks.
+  value   whole-job GFLOP/s with the operands resident in HBM (bof_sgemm_f32: operand split of both
+          matrices + the tcgen05 kernel), CUDA-event timed, max over ranks.
   e2e     the same metric through the host entry point bof_host_gemm (what flash::gemm calls):
           pinned host buffers, H2D of A-shard and B and D2H of C inside the timed region.
   roofline  dominant kernel gemm3xtf32_kernel: useful flops 2*m*n*k per launch / its CUDA-event
-          duration, against TF32_peak/3 with TF32_peak = bf16 measured peak / 2 (sustained figure
-          of MEASURED_PEAKS.json: the kernel runs ~0.5 s per launch).
+          duration, against 1/(1/TF32 + 2/BF16) (one tf32 and two bf16 MMAs per product), BF16 from
+          MEASURED_PEAKS.json, TF32 from a cuBLAS measurement in the same run (sustained figures:
+          the kernel runs ~0.2 s per launch).
   cpu_baseline  MKL sgemm (oneMKL from libtorch_cpu, the library family the reference calls) on
           the box's host cores on a bounded sample: one 8192^3 GemmTask tile (1/64 of the job).
   extra   csrmm cfg-1 (configs[0]) device-resident SpMM numbers with the HBM roofline.
@@ -42,7 +43,7 @@ if "--impl" in sys.argv and "reference" in sys.argv:
 M_FULL = N_FULL = K_FULL = 32768
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size gemm3xtf32_kernel launch, from the
 # ncu --set full capture summarised in profiles/ (None until that capture exists)
-NCU_TRAFFIC_BYTES = 275563161856 + 4640736768  # profiles/r01/ncu_gemm32k_sync.csv (trip 5)
+NCU_TRAFFIC_BYTES = 275547808768 + 4636467712  # profiles/r01/ncu_gemm32k_hybrid.csv (trip 9)
 TILE = 8192  # reference GEMM_BLK_SIZE (CMakeLists.txt:46-50 of the reference)
 
 
@@ -286,15 +287,19 @@ def main():
     achieved = 2.0 * Mr * Ng * Kg / t_kernel / 1e12
     tf32 = tf32_library_peak(torch)
     # the kernel runs for ~0.3 s per launch under the power cap -> sustained figure; a short debug size -> burst
-    tf32_peak = tf32["sustained"] if t_kernel > 0.05 else tf32["burst"]
-    bf16_sixth = (pk["bf16_sustained"] if t_kernel > 0.05 else pk["bf16_burst"]) / 6.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
-                "frac": achieved / (tf32_peak / 3.0), "traffic": NCU_TRAFFIC_BYTES,
-                "kernel": "gemm3xtf32_kernel<2,EPI_GEMM,chunked>", "kernel_ms": t_kernel * 1e3,
-                "peak_note": "useful fp32 flops (2mnk) against TF32_peak/3; TF32_peak = cuBLAS TF32 8192^3 measured in this "
-                             f"run (burst {tf32['burst']:.0f}, sustained {tf32['sustained']:.0f} TFLOP/s) because "
-                             "MEASURED_PEAKS.json only carries bf16",
-                "alt_peak_bf16_div_6": bf16_sixth, "alt_frac": achieved / bf16_sixth, "peaks_file": pk["src"]}
+    long_run = t_kernel > 0.05
+    tf32_peak = tf32["sustained"] if long_run else tf32["burst"]
+    bf16_peak = pk["bf16_sustained"] if long_run else pk["bf16_burst"]
+    # per useful flop the kernel issues one TF32 MMA flop (hi*hi) and two BF16 MMA flops (the cross terms)
+    peak = 1.0 / (1.0 / tf32_peak + 2.0 / bf16_peak)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                "kernel": "gemm3xtf32_kernel<2,EPI_GEMM,chunked,hybrid>", "kernel_ms": t_kernel * 1e3,
+                "peak_note": "useful fp32 flops (2mnk) per launch against 1/(1/TF32 + 2/BF16): one tf32 MMA (hi*hi) and two "
+                             f"bf16 MMAs (cross terms) per product; BF16 = MEASURED_PEAKS.json ({pk['src']}) "
+                             f"{'sustained' if long_run else 'burst'} {bf16_peak:.0f}, TF32 = cuBLAS TF32 8192^3 measured in this "
+                             f"run (burst {tf32['burst']:.0f}, sustained {tf32['sustained']:.0f} TFLOP/s; the file has no TF32 entry)",
+                "alt_peak_3xtf32": tf32_peak / 3.0, "alt_frac_3xtf32": achieved / (tf32_peak / 3.0), "peaks_file": pk["src"]}
     # spot check of the result on the timed buffers (cheap: 64 sampled entries in fp64)
     ii = torch.randint(0, Mr, (64,), device="cuda"); jj = torch.randint(0, Ng, (64,), device="cuda")
     ref = (A[ii].double() * B[:, jj].t().double()).sum(1)
@@ -351,7 +356,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"flash::gemm sgemm {Mg}x{Ng}x{Kg} fp32 row-major NN alpha=1 beta=0 (BASELINE.json configs[1])",
                        "sharding": f"C/A row blocks over {world} rank(s), B replicated, no collective",
-                       "arithmetic": "3xTF32 (hi/lo split, lo*hi + hi*lo + hi*hi) on tcgen05, fp32 accumulate",
+                       "arithmetic": "three-term split on tcgen05: hi*hi kind::tf32 + (lo*hi, hi*lo) on bf16 copies kind::f16, fp32 "
+                                     "accumulate in TMEM folded in fp32 registers every 256 k",
                        "l2": "operands (4 GiB each) exceed the 126 MB L2; no flush needed",
                        "spot_check_max_rel_err": spot},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
