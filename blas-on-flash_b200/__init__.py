@@ -144,6 +144,14 @@ class Context:
         self._check(self.lib.bof_host_gemm(self.h, ch(ord_), ch(ta), ch(tb), m, n, k, alpha, beta, ptr(a), ptr(b),
                                            ptr(c), lda, ldb, ldc))
 
+    def host_gemm_devb(self, ta, tb, m, n, k, alpha, beta, a, b_dev, c, lda=0, ldb=0, ldc=0):
+        self._check(self.lib.bof_host_gemm_devb(self.h, ch(ta), ch(tb), m, n, k, alpha, beta, ptr(a), ptr(b_dev),
+                                                ptr(c), lda, ldb, ldc))
+
+    def host_csrmm_devb(self, m, n, k, alpha, beta, a, ia, ja, b_dev, c):
+        self._check(self.lib.bof_host_csrmm_devb(self.h, m, n, k, alpha, beta, ptr(a), ptr(ia), ptr(ja), ptr(b_dev),
+                                                 ptr(c)))
+
     def host_csrgemv(self, trans_a, m, n, a, ia, ja, b, c):
         self._check(self.lib.bof_host_csrgemv(self.h, ch(trans_a), m, n, ptr(a), ptr(ia), ptr(ja), ptr(b), ptr(c)))
 

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "bof_last_error": (C.c_char_p, [_vp]),
     "bof_get_stats": (C.c_int, [_vp, C.POINTER(BofStats)]),
     "bof_launch_count": (_i64, [_vp]),
+    "bof_register_mapping": (C.c_int, [_vp, _sz, C.c_int, C.c_uint64]),
+    "bof_unregister_mapping": (C.c_int, [_vp]),
     "bof_spmm_csr_f32": (C.c_int, [_vp, _vp, _ch, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _i64, _f32,
                                    _vp, _i64, _vp, _sz]),
     "bof_spmm_workspace_bytes": (_sz, [_ch, _i64, _i64, _i64]),
@@ -77,6 +79,8 @@ PROTOTYPES = {
     "bof_host_csrmm": (C.c_int, [_vp, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _ch, _vp, _vp]),
     "bof_host_gemm": (C.c_int, [_vp, _ch, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64,
                                 _i64]),
+    "bof_host_gemm_devb": (C.c_int, [_vp, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "bof_host_csrmm_devb": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "bof_host_csrgemv": (C.c_int, [_vp, _ch, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "bof_host_csrcsc": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bof_kmeans_open": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, C.POINTER(_vp)]),

@@ -56,3 +56,27 @@ def lloyd(km, iters: int, group=None):
             with torch.cuda.stream(stream):
                 dist.all_reduce(as_tensor(ptr, count, km.ctx.device), op=dist.ReduceOp.SUM, group=group)
         km.update()
+
+
+def allgather_dense(host_full, out_dev, group=None):
+    """Assemble a replicated row-major dense operand in every rank's HBM with 1/G of the PCIe traffic:
+    rank r uploads rows row_shard(r) of `host_full` (a host tensor every rank can read, e.g. the mmap of
+    the same file) into its slice of `out_dev`, then the slices are exchanged over NVLink.
+    Returns the bytes this rank moved over PCIe."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rows = host_full.shape[0]
+    r0, r1 = row_shard(rows, world, rank)
+    out_dev[r0:r1].copy_(host_full[r0:r1], non_blocking=True)
+    if world > 1:
+        if rows % world == 0:
+            dist.all_gather_into_tensor(out_dev, out_dev[r0:r1], group=group)
+        else:  # uneven shards: one broadcast per owner
+            for src in range(world):
+                s0, s1 = row_shard(rows, world, src)
+                dist.broadcast(out_dev[s0:s1], src=src, group=group)
+    torch.cuda.current_stream().synchronize()  # the library's streams do not know about this one
+    return (r1 - r0) * host_full[0].numel() * host_full.element_size()

@@ -48,7 +48,7 @@ typedef struct bof_ctx bof_ctx;
  * where a counterpart exists.  Zero in any field selects the default. */
 typedef struct bof_config {
   int32_t device;            /* CUDA ordinal this context drives (one context per GPU/process)  */
-  int32_t n_copy_threads;    /* host staging threads (reference N_IO_THR=4)                     */
+  int32_t n_copy_threads;    /* host staging threads (reference N_IO_THR=4; default 8)          */
   uint64_t stage_bytes;      /* bytes per pinned staging buffer (default 16 MiB)                */
   int32_t n_stage_bufs;      /* pinned ring depth per direction (default 4)                     */
   uint64_t csrmm_max_nnz;    /* nnz budget per streamed CSR row block (reference MAX_NNZS=1e7;
@@ -86,6 +86,13 @@ const char* bof_last_error(const bof_ctx* ctx);
 int bof_get_stats(const bof_ctx* ctx, bof_stats* out);
 /* Total kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t bof_launch_count(const bof_ctx* ctx);
+/* Tell the library that host range [base, base+len) is the mmap of descriptor `fd` starting at byte
+ * `file_offset` (what map_file() creates, include/pointers/allocator.h:19-45).  Host entry points then
+ * move such operands with pread/pwrite into their pinned staging buffers -- the reference's
+ * FlashFileHandle::read/write into cache buffers (src/file_handles/flash_file_handle.cpp:247-407) --
+ * instead of faulting the mapping page by page.  Process-wide; include/pointers/allocator.h calls it. */
+int bof_register_mapping(const void* base, size_t len, int fd, uint64_t file_offset);
+int bof_unregister_mapping(const void* base);
 /* ABI version, bumped on any signature change. */
 int bof_abi_version(void);
 
@@ -187,6 +194,17 @@ int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, 
 int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
                   float alpha, float beta, const float* a, const float* b, float* c, int64_t lda,
                   int64_t ldb, int64_t ldc);
+
+/* Variants for one-process-per-GPU sharding with the replicated dense operand already in this GPU's
+ * HBM: every rank uploads only 1/G of B and the ranks all-gather the rest over NVLink
+ * (ncclAllGather, or blas-on-flash_b200/dist.py::allgather_dense); only the sharded operand and the
+ * output rows cross PCIe.  b_dev is read-only.  Row-major, csrmm trans_a='N' only. */
+int bof_host_gemm_devb(bof_ctx* ctx, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
+                       float beta, const float* a, const float* b_dev, float* c, int64_t lda,
+                       int64_t ldb, int64_t ldc);
+int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alpha, float beta,
+                        const float* a, const int64_t* ia, const int64_t* ja, const float* b_dev,
+                        float* c);
 
 /* flash::csrgemv (include/flash_blas.h:55-57; src/blas/csrgemv.cpp:82-97). */
 int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a,

@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "bof_b200.h"
 #include "file_handles/flash_file_handle.h"
 #include "pointers/pointer.h"
 
@@ -30,6 +31,8 @@ flash_ptr<T> map_file(std::string fname, Mode mode, FBLAS_UINT foffset = 0, int 
     delete fh;
     throw std::runtime_error("map_file: mmap of " + fname + " failed: " + std::strerror(errno));
   }
+  // let the GPU pipeline stage this file with pread/pwrite instead of faulting the mapping page by page
+  bof_register_mapping(base, fh->file_sz, fh->file_desc, 0);
   return flash_ptr<T>(reinterpret_cast<T*>(static_cast<char*>(base) + foffset), foffset, fh);
 }
 
@@ -37,6 +40,7 @@ template <typename T>
 void unmap_file(flash_ptr<T> fptr) {
   auto* fh = dynamic_cast<FlashFileHandle*>(fptr.fop);
   if (fh == nullptr) return;
+  bof_unregister_mapping(reinterpret_cast<char*>(fptr.ptr) - fptr.foffset);
   ::munmap(reinterpret_cast<char*>(fptr.ptr) - fptr.foffset, fh->file_sz);
   delete fh;
 }

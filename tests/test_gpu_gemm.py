@@ -197,6 +197,27 @@ def test_host_gemm(bof, ord_, ta, tb):
         assert st.h2d_bytes >= (M * K + K * N + M * N) * 4 and st.d2h_bytes == M * N * 4
 
 
+def test_host_devb_variants(ctx):
+    """Replicated operand already in HBM (the all-gather path of multi-GPU runs): same results as the host path."""
+    rng = np.random.default_rng(8)
+    M, N, K = 900, 640, 500
+    A = rng.random((M, K), dtype=np.float32); B = rng.random((K, N), dtype=np.float32)
+    C0 = rng.random((M, N), dtype=np.float32)
+    c_h = C0.copy()
+    ctx.host_gemm_devb("N", "N", M, N, K, 1.5, 0.5, A, dev(B), c_h)
+    assert oracle.rel_fro(c_h, oracle.gemm("R", "N", "N", M, N, K, 1.5, 0.5, A, B, C0, acc64=True)) <= TOL
+    c_h = C0.copy()
+    ctx.host_gemm_devb("N", "T", M, N, K, 1.0, 0.0, A, dev(np.ascontiguousarray(B.T)), c_h)
+    assert oracle.rel_fro(c_h, oracle.gemm("R", "N", "N", M, N, K, 1.0, 0.0, A, B, C0, acc64=True)) <= TOL
+    from gpu_util import ragged_csr
+    m, n, k = 2000, 1500, 64
+    a, ia, ja = ragged_csr(rng, m, n, 40)
+    Bd = rng.random((n, k), dtype=np.float32)
+    c2 = np.full((m, k), np.nan, np.float32)
+    ctx.host_csrmm_devb(m, n, k, 1.0, 0.0, a, ia, ja, dev(Bd), c2)
+    assert oracle.rel_fro(c2, oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", Bd, np.zeros((m, k), np.float32), acc64=True)) <= TOL
+
+
 def test_host_gemm_bad_args(ctx):
     from bof_b200 import ptr
     z = np.zeros(4, np.float32)
