@@ -176,7 +176,8 @@ void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_
   int fd = -1;
   uint64_t foff = 0;
   const size_t span = rows == 0 ? 0 : (rows - 1) * hpitch + width;
-  const bool via_fd = lookup_mapping(host, span, &fd, &foff);
+  static const bool no_fd = getenv("BOF_NO_FD") != nullptr;  // A/B switch: copy through the mapping instead
+  const bool via_fd = !no_fd && lookup_mapping(host, span, &fd, &foff);
   ctx->pool->run(parts, [&](int part) {
     if (hpitch == width) {  // flat: split by bytes
       const size_t b0 = total * part / parts, b1 = total * (part + 1) / parts;

@@ -48,8 +48,9 @@ struct StopWatch {
 inline void report(const char* what, double secs, FBLAS_INT rc) {
   bof_stats st{};
   if (bof_ctx* ctx = flash::flash_context()) bof_get_stats(ctx, &st);
-  std::printf("%s took %.3f s, returned %lld; h2d %.1f MB, d2h %.1f MB, kernels %lld\n", what, secs, (long long)rc,
-              st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, (long long)st.kernel_launches);
+  std::printf("%s took %.3f s, returned %lld; h2d %.1f MB, d2h %.1f MB, kernels %lld, host staging in %.0f ms / out %.0f ms, "
+              "library wall %.0f ms\n", what, secs, (long long)rc, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6,
+              (long long)st.kernel_launches, st.stage_in_ms, st.stage_out_ms, st.total_ms);
 }
 
 }  // namespace drv

@@ -71,6 +71,14 @@ def main():
                      "process_wall_s": wall, "file_gbs_both_ways": 2 * (nnz * 12 + (n + 1) * 8) / secs / 1e9,
                      "offsets_end_equals_nnz": bool(offs_t[-1] == nnz and offs_t[0] == 0), "driver_says": line})
         print(json.dumps(recs[-1]), flush=True)
+        if os.environ.get("BOF_AB"):
+            env = dict(os.environ, BOF_NO_FD="1")
+            secs, wall, line = run("csrmm", d / "A.csr", d / "A.col", d / "A.off", d / "B.bin", d / "C.bin", m, n, a.k, 1.0, 0.0, "N", "R", env=env)
+            recs.append({"config": "drivers/csrmm again with BOF_NO_FD=1 (memcpy through the mapping)", "flash_csrmm_s": secs, "driver_says": line})
+            print(json.dumps(recs[-1]), flush=True)
+            secs, wall, line = run("csrmm", d / "A.csr", d / "A.col", d / "A.off", d / "B.bin", d / "C.bin", m, n, a.k, 1.0, 0.0, "N", "R")
+            recs.append({"config": "drivers/csrmm third run (fd path, C file now fully allocated)", "flash_csrmm_s": secs, "driver_says": line})
+            print(json.dumps(recs[-1]), flush=True)
         for f in ("A.csr", "A.col", "A.off", "B.bin", "C.bin", "T.csr", "T.col", "T.off"):
             (d / f).unlink(missing_ok=True)
         # ---- gemm ----
