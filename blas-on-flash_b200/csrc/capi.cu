@@ -262,7 +262,8 @@ int copy2d(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitc
   if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (double)width * height;
   else if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += (double)width * height;
   const void* host = kind == cudaMemcpyHostToDevice ? src : dst;
-  const bool staged = width * height >= (256u << 10) && width <= ctx->cfg.stage_bytes && !host_is_pinned(host);
+  const bool flat = (dpitch == width && spitch == width) || height == 1;
+  const bool staged = width * height >= (256u << 10) && (flat || width <= ctx->cfg.stage_bytes) && !host_is_pinned(host);
   if (staged) return staged_copy(ctx, dst, dpitch, src, spitch, width, height, kind, s);
   if (dpitch == width && spitch == width) {
     BOF_CUDA(ctx, cudaMemcpyAsync(dst, src, width * height, kind, s));

@@ -34,6 +34,16 @@ def run(exe, *args, env=None):
     return float(m.group(1)), wall, r.stdout.strip().splitlines()[-1]
 
 
+def prealloc(path, nbytes):
+    """Output files are pre-allocated, as misc/gemm_run.sh:17-18 does with `fallocate -l` (a sparse file would
+    charge page allocation to the first write)."""
+    fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o666)
+    try:
+        os.posix_fallocate(fd, 0, nbytes)
+    finally:
+        os.close(fd)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dir", default="/dev/shm/bof")
@@ -51,7 +61,7 @@ def main():
         B = torch.rand((n, a.k), device="cuda")
         vals.cpu().numpy().tofile(d / "A.csr"); idx.cpu().numpy().astype(np.int64).tofile(d / "A.col")
         offs.cpu().numpy().tofile(d / "A.off"); B.cpu().numpy().tofile(d / "B.bin")
-        np.zeros(1, np.float32).tofile(d / "C.bin"); os.truncate(d / "C.bin", m * a.k * 4)
+        prealloc(d / "C.bin", m * a.k * 4)
         colsum = torch.zeros(n, device="cuda", dtype=torch.float64).index_add_(0, idx.long(), vals.double())
         want = float((colsum * B.double().sum(1)).sum())
         nnz = m * a.nnz_per_row
@@ -85,7 +95,7 @@ def main():
         g = a.gemm
         A = torch.rand((g, g), device="cuda"); Bm = torch.rand((g, g), device="cuda")
         A.cpu().numpy().tofile(d / "GA.bin"); Bm.cpu().numpy().tofile(d / "GB.bin")
-        np.zeros(1, np.float32).tofile(d / "GC.bin"); os.truncate(d / "GC.bin", g * g * 4)
+        prealloc(d / "GC.bin", g * g * 4)
         want = float((A.double().sum(0) * Bm.double().sum(1)).sum())
         del A, Bm
         torch.cuda.empty_cache()
