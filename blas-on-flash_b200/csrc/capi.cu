@@ -139,9 +139,9 @@ int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
 }
 
 // File-backed host ranges registered by the flash:: layer (map_file): base address -> (length, fd, file offset
-// of the base).  Staging copies for such ranges use pread/pwrite on the descriptor instead of touching the
-// mapping, which would take one minor page fault per 4 KiB (measured 3-9 GB/s against 30+ GB/s for pread
-// from the page cache with 8 threads).  The page cache keeps both views coherent.
+// of the base).  With BOF_STAGE_FD=1 staging copies for such ranges use pread/pwrite on the descriptor instead
+// of touching the mapping (the reference's FlashFileHandle::read/write into cache buffers); the page cache keeps
+// both views coherent.
 struct FileRange { size_t len; int fd; uint64_t file_off; };
 std::mutex g_map_mu;
 std::map<uintptr_t, FileRange> g_mappings;
@@ -176,8 +176,12 @@ void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_
   int fd = -1;
   uint64_t foff = 0;
   const size_t span = rows == 0 ? 0 : (rows - 1) * hpitch + width;
-  static const bool no_fd = getenv("BOF_NO_FD") != nullptr;  // A/B switch: copy through the mapping instead
-  const bool via_fd = !no_fd && lookup_mapping(host, span, &fd, &foff);
+  // Measured on the B200 boxes with page-cache-resident files (profiles/r01/trip12_driver_ab.txt): 8 workers
+  // copying through the mapping move 44 GB/s in and 19 GB/s out, pread/pwrite 29 / 5.7 GB/s (pwrite to tmpfs
+  // is the slow one).  The descriptor path therefore stays opt-in (BOF_STAGE_FD=1) for cold files on real disks,
+  // where explicit large reads beat 4 KiB fault-driven readahead.
+  static const bool use_fd = getenv("BOF_STAGE_FD") != nullptr;
+  const bool via_fd = use_fd && lookup_mapping(host, span, &fd, &foff);
   ctx->pool->run(parts, [&](int part) {
     if (hpitch == width) {  // flat: split by bytes
       const size_t b0 = total * part / parts, b1 = total * (part + 1) / parts;

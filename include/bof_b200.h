@@ -87,10 +87,11 @@ int bof_get_stats(const bof_ctx* ctx, bof_stats* out);
 /* Total kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t bof_launch_count(const bof_ctx* ctx);
 /* Tell the library that host range [base, base+len) is the mmap of descriptor `fd` starting at byte
- * `file_offset` (what map_file() creates, include/pointers/allocator.h:19-45).  Host entry points then
- * move such operands with pread/pwrite into their pinned staging buffers -- the reference's
- * FlashFileHandle::read/write into cache buffers (src/file_handles/flash_file_handle.cpp:247-407) --
- * instead of faulting the mapping page by page.  Process-wide; include/pointers/allocator.h calls it. */
+ * `file_offset` (what map_file() creates, include/pointers/allocator.h:19-45).  With BOF_STAGE_FD=1 in the
+ * environment host entry points move such operands with pread/pwrite into their pinned staging buffers --
+ * the reference's FlashFileHandle::read/write into cache buffers (src/file_handles/flash_file_handle.cpp:
+ * 247-407) -- which pays off for cold files on real disks; by default they copy through the mapping, the
+ * faster way for page-cache-resident files (measured).  Process-wide; include/pointers/allocator.h calls it. */
 int bof_register_mapping(const void* base, size_t len, int fd, uint64_t file_offset);
 int bof_unregister_mapping(const void* base);
 /* ABI version, bumped on any signature change. */
