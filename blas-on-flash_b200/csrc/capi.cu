@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <map>
 #include <thread>
@@ -71,6 +72,75 @@ class CopyPool {
   int parts_ = 0, pending_ = 0;
   uint64_t epoch_ = 0;
   bool stop_ = false;
+};
+
+void drain_copy_out(bof_ctx* ctx, StageSlot* sl);  // defined below (needs host_rows_copy)
+
+// One background thread per context: waits for a device->host chunk to land in its pinned slot, copies it
+// to the caller's (pageable) buffer and returns the slot to the ring, so that the calling thread can keep
+// staging uploads meanwhile.  The writer side of the reference's IoExecutor threads.
+class Drainer {
+ public:
+  explicit Drainer(bof_ctx* ctx) : ctx_(ctx), th_([this] { loop(); }) {}
+  ~Drainer() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    th_.join();
+  }
+  void wait_free(StageSlot& sl) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_free_.wait(lk, [&] { return !sl.in_flight; });
+  }
+  void push(StageSlot* sl) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      sl->in_flight = true;
+      q_.push_back(sl);
+    }
+    cv_.notify_one();
+  }
+  bool wait_idle() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_free_.wait(lk, [&] { return q_.empty() && !busy_; });
+    const bool ok = ok_;
+    ok_ = true;
+    return ok;
+  }
+
+ private:
+  void loop() {
+    cudaSetDevice(ctx_->device);
+    for (;;) {
+      StageSlot* sl = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;  // stop requested and nothing left
+        sl = q_.front();
+        q_.pop_front();
+        busy_ = true;
+      }
+      const bool landed = cudaEventSynchronize(sl->ev) == cudaSuccess;
+      if (landed) drain_copy_out(ctx_, sl);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!landed) ok_ = false;
+        sl->in_flight = false;
+        sl->out_dst = nullptr;
+        busy_ = false;
+      }
+      cv_free_.notify_all();
+    }
+  }
+  bof_ctx* ctx_;
+  std::mutex mu_;
+  std::condition_variable cv_, cv_free_;
+  std::deque<StageSlot*> q_;
+  bool stop_ = false, busy_ = false, ok_ = true;
+  std::thread th_;
 };
 }  // namespace bof
 
@@ -135,6 +205,8 @@ int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
     BOF_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
   }
   if (!ctx->pool) ctx->pool = new CopyPool(ctx->cfg.n_copy_threads);
+  if (!ctx->pool_out) ctx->pool_out = new CopyPool(ctx->cfg.n_copy_threads);
+  if (!ctx->drainer) ctx->drainer = new Drainer(ctx);
   return BOF_OK;
 }
 
@@ -172,7 +244,8 @@ bool file_xfer(bool write, int fd, char* buf, size_t len, uint64_t off) {
 void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_t width, size_t rows, bool to_packed) {
   const double t0 = now_ms();
   const size_t total = width * rows;
-  const int parts = (int)std::min<size_t>((size_t)ctx->pool->size(), std::max<size_t>(1, total >> 20));
+  CopyPool* pool = to_packed ? ctx->pool : ctx->pool_out;  // the two directions run on different threads
+  const int parts = (int)std::min<size_t>((size_t)pool->size(), std::max<size_t>(1, total >> 20));
   int fd = -1;
   uint64_t foff = 0;
   const size_t span = rows == 0 ? 0 : (rows - 1) * hpitch + width;
@@ -182,7 +255,7 @@ void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_
   // where explicit large reads beat 4 KiB fault-driven readahead.
   static const bool use_fd = getenv("BOF_STAGE_FD") != nullptr;
   const bool via_fd = use_fd && lookup_mapping(host, span, &fd, &foff);
-  ctx->pool->run(parts, [&](int part) {
+  pool->run(parts, [&](int part) {
     if (hpitch == width) {  // flat: split by bytes
       const size_t b0 = total * part / parts, b1 = total * (part + 1) / parts;
       if (via_fd && file_xfer(!to_packed, fd, packed + b0, b1 - b0, foff + b0)) return;
@@ -200,14 +273,19 @@ void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_
   (to_packed ? ctx->stats.stage_in_ms : ctx->stats.stage_out_ms) += now_ms() - t0;
 }
 
+}  // namespace
+namespace bof {
+void drain_copy_out(bof_ctx* ctx, StageSlot* sl) {
+  if (sl->out_dst)
+    host_rows_copy(ctx, static_cast<char*>(sl->ptr), sl->out_dst, sl->out_pitch, sl->out_width, sl->out_rows, false);
+}
+}  // namespace bof
+namespace {
+// host -> device slots are recycled by the calling thread once their DMA has finished
 int drain_slot(bof_ctx* ctx, StageSlot& sl) {
   if (!sl.in_flight) return BOF_OK;
   BOF_CUDA(ctx, cudaEventSynchronize(sl.ev));
   sl.in_flight = false;
-  if (sl.out_dst) {
-    host_rows_copy(ctx, static_cast<char*>(sl.ptr), sl.out_dst, sl.out_pitch, sl.out_width, sl.out_rows, false);
-    sl.out_dst = nullptr;
-  }
   return BOF_OK;
 }
 
@@ -233,7 +311,8 @@ int staged_copy(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t 
   for (size_t r0 = 0; r0 < total_rows; r0 += rows_per_chunk, ++slot_i) {
     const size_t rows = std::min(rows_per_chunk, total_rows - r0);
     StageSlot& sl = ring[slot_i % ring.size()];
-    BOF_TRY(drain_slot(ctx, sl));
+    if (h2d) BOF_TRY(drain_slot(ctx, sl));
+    else ctx->drainer->wait_free(sl);  // the drainer thread hands the slot back after copying it out
     // the last pseudo row of a flat transfer may be short
     const size_t bytes = flat ? std::min(flat_bytes - r0 * w, rows * w) : rows * w;
     if (h2d) {
@@ -251,10 +330,9 @@ int staged_copy(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t 
       }
     }
     BOF_CUDA(ctx, cudaEventRecord(sl.ev, s));
-    sl.in_flight = true;
+    if (h2d) sl.in_flight = true;
+    else ctx->drainer->push(&sl);  // copied out in the background; sync_all()/drain_wait() joins
   }
-  if (!h2d)
-    for (size_t i = 0; i < ring.size(); ++i) BOF_TRY(drain_slot(ctx, ring[(slot_i + i) % ring.size()]));
   return BOF_OK;
 }
 
@@ -290,11 +368,17 @@ void stats_end(bof_ctx* ctx) {
   ctx->stats.kernel_launches += ctx->launches.load();
 }
 
+// all staged device->host chunks have reached the caller's buffer
+int drain_wait(bof_ctx* ctx) {
+  if (ctx->drainer && !ctx->drainer->wait_idle()) return fail(ctx, BOF_ECUDA, "device->host staging failed");
+  return BOF_OK;
+}
+
 int sync_all(bof_ctx* ctx) {
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
-  return BOF_OK;
+  return drain_wait(ctx);
 }
 
 
@@ -481,12 +565,14 @@ int bof_ctx_destroy(bof_ctx* ctx) {
   for (int i = 0; i < bof_ctx::kSlots; ++i)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
+  delete ctx->drainer;  // joins its thread before the rings go away
+  delete ctx->pool;
+  delete ctx->pool_out;
   for (auto* ring : {&ctx->stage_in, &ctx->stage_out})
     for (auto& sl : *ring) {
       if (sl.ptr) cudaFreeHost(sl.ptr);
       if (sl.ev) cudaEventDestroy(sl.ev);
     }
-  delete ctx->pool;
   if (ctx->sync_ctr) cudaFree(ctx->sync_ctr);
   if (ctx->tk0) cudaEventDestroy(ctx->tk0);
   if (ctx->tk1) cudaEventDestroy(ctx->tk1);
@@ -1257,7 +1343,7 @@ int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host) {
     BOF_TRY(copy1d(ctx, assign_host, km->assign64, (size_t)km->npoints * 8, cudaMemcpyDeviceToHost, s));
   }
   BOF_CUDA(ctx, cudaStreamSynchronize(s));
-  return BOF_OK;
+  return drain_wait(ctx);
 }
 
 void* bof_kmeans_stream(bof_kmeans* km) { return km ? (void*)km->ctx->compute : nullptr; }

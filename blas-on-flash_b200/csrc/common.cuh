@@ -30,6 +30,7 @@ struct StageSlot {
 };
 
 class CopyPool;  // host memcpy worker threads (capi.cu)
+class Drainer;   // background thread that copies landed device->host chunks out of the pinned ring (capi.cu)
 
 }  // namespace bof
 
@@ -44,7 +45,9 @@ struct bof_ctx {
   cudaStream_t h2d = nullptr;      // uploads
   cudaStream_t d2h = nullptr;      // downloads
   std::vector<bof::StageSlot> stage_in, stage_out;   // pinned rings, allocated on first pageable copy
-  bof::CopyPool* pool = nullptr;
+  bof::CopyPool* pool = nullptr;       // workers of the calling thread (host -> pinned)
+  bof::CopyPool* pool_out = nullptr;   // workers of the drainer thread (pinned -> host)
+  bof::Drainer* drainer = nullptr;
   std::string err;
   bof_stats stats{};
   std::atomic<int64_t> launches{0};
