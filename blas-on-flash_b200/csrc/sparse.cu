@@ -30,8 +30,10 @@ __device__ __forceinline__ void fma4(float4& acc, float v, const float4& b) {
 // L lanes per row, KV float4 per lane: one pass covers 4*L*KV columns starting at
 // blockIdx.y * 4*L*KV.  Requires B, C 16-byte aligned, ldb/ldc multiples of 4; the column
 // tail (k not a multiple of 4*L) is masked per float4, k itself must be a multiple of 4.
-template <int L, int KV>
-__global__ void __launch_bounds__(256)
+// U = B rows in flight per row group (registers), MINB = resident blocks per SM the register budget is cut
+// for: together they set the bytes in flight per SM, which is what bounds this latency-limited gather.
+template <int L, int KV, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
                        const int32_t* __restrict__ idx, const int64_t* __restrict__ offs,
                        const float* __restrict__ B, int64_t ldb, float beta, float* __restrict__ C,
@@ -73,24 +75,24 @@ spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restric
     // a == 0 for the padded lanes, so the full-width loop below is safe: it gathers row
     // idx 0 of B at most L-1 extra times on the last chunk; keep it exact instead:
     int t = 0;
-    for (; t + 4 <= cnt; t += 4) {
-      int32_t cc[4];
-      float aa[4];
-      float4 bb[4][KV];
+    for (; t + U <= cnt; t += U) {
+      int32_t cc[U];
+      float aa[U];
+      float4 bb[U][KV];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         cc[u] = __shfl_sync(gmask, c, t + u, L);
         aa[u] = __shfl_sync(gmask, a, t + u, L);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const float* brow = B + (int64_t)cc[u] * ldb + col0;
 #pragma unroll
         for (int v = 0; v < KV; ++v)
           bb[u][v] = col_ok[v] ? ldg_f4(brow + v * 4 * L) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int v = 0; v < KV; ++v) fma4(acc[v], aa[u], bb[u][v]);
     }
@@ -273,15 +275,15 @@ transpose_kernel(int64_t rows, int64_t cols, float alpha, const float* __restric
   }
 }
 
-template <int L, int KV>
+template <int L, int KV, int U = 4, int MINB = 4>
 int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                     const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
                     int64_t ldb, float beta, float* C, int64_t ldc) {
   constexpr int ROWS_PER_BLOCK = 8 * (32 / L);
   dim3 grid((unsigned)ceil_div<int64_t>(m, ROWS_PER_BLOCK),
             (unsigned)ceil_div<int64_t>(k, 4 * L * KV));
-  spmm_csr_rm_vec_kernel<L, KV><<<grid, 256, 0, s>>>(m, k, alpha, vals, idx, offs, B, ldb, beta,
-                                                     C, ldc);
+  spmm_csr_rm_vec_kernel<L, KV, U, MINB><<<grid, 256, 0, s>>>(m, k, alpha, vals, idx, offs, B, ldb, beta,
+                                                              C, ldc);
   BOF_LAUNCH_CHECK(ctx, "spmm_csr_rm_vec_kernel");
   return BOF_OK;
 }
@@ -305,8 +307,29 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
   if (k <= 16) BOF_SPMM(4, 1);
   if (k <= 32) BOF_SPMM(8, 1);
   if (k <= 64) BOF_SPMM(16, 1);
-  if (k <= 128) BOF_SPMM(32, 1);
-  BOF_SPMM(32, 2);
+  // tuning switch for the two wide shapes (profiles/: variant sweep); default = variant 0
+  static const int variant = getenv("BOF_SPMM_VARIANT") ? atoi(getenv("BOF_SPMM_VARIANT")) : 0;
+#define BOF_SPMM_V(L, KV, U, MINB) \
+  return spmm_vec_launch<L, KV, U, MINB>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
+  if (k <= 128) {
+    switch (variant) {
+      case 1: BOF_SPMM_V(32, 1, 4, 5);
+      case 2: BOF_SPMM_V(32, 1, 4, 6);
+      case 3: BOF_SPMM_V(32, 1, 8, 3);
+      case 4: BOF_SPMM_V(32, 1, 8, 4);
+      case 5: BOF_SPMM_V(32, 1, 16, 2);
+      default: BOF_SPMM_V(32, 1, 4, 4);
+    }
+  }
+  switch (variant) {
+    case 1: BOF_SPMM_V(32, 2, 4, 5);
+    case 2: BOF_SPMM_V(32, 2, 4, 6);
+    case 3: BOF_SPMM_V(32, 2, 8, 3);
+    case 4: BOF_SPMM_V(32, 2, 8, 4);
+    case 5: BOF_SPMM_V(32, 2, 16, 2);
+    default: BOF_SPMM_V(32, 2, 4, 4);
+  }
+#undef BOF_SPMM_V
 #undef BOF_SPMM
 }
 
