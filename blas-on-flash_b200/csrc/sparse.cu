@@ -307,8 +307,10 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
   if (k <= 16) BOF_SPMM(4, 1);
   if (k <= 32) BOF_SPMM(8, 1);
   if (k <= 64) BOF_SPMM(16, 1);
-  // tuning switch for the two wide shapes (profiles/: variant sweep); default = variant 0
-  static const int variant = getenv("BOF_SPMM_VARIANT") ? atoi(getenv("BOF_SPMM_VARIANT")) : 0;
+  // Bytes-in-flight tuning of the two wide shapes (profiles/r01/spmm_variants.txt): with B ~ L2-sized (cfg-1)
+  // 8 rows in flight at 4 blocks/SM is 31 % faster than 4 rows; with B >> L2 (cfg-3) every variant sits at the
+  // DRAM gather limit.  BOF_SPMM_VARIANT overrides (0..5) for experiments.
+  static const int variant = getenv("BOF_SPMM_VARIANT") ? atoi(getenv("BOF_SPMM_VARIANT")) : -1;
 #define BOF_SPMM_V(L, KV, U, MINB) \
   return spmm_vec_launch<L, KV, U, MINB>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
   if (k <= 128) {
@@ -318,7 +320,8 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
       case 3: BOF_SPMM_V(32, 1, 8, 3);
       case 4: BOF_SPMM_V(32, 1, 8, 4);
       case 5: BOF_SPMM_V(32, 1, 16, 2);
-      default: BOF_SPMM_V(32, 1, 4, 4);
+      case 0: BOF_SPMM_V(32, 1, 4, 4);
+      default: BOF_SPMM_V(32, 1, 8, 4);
     }
   }
   switch (variant) {
