@@ -311,9 +311,12 @@ def main():
     Ah = torch.empty((Mr, Kg), dtype=torch.float32, pin_memory=True)
     Bh = torch.empty((Kg, Ng), dtype=torch.float32, pin_memory=True)
     Ch = torch.empty((Mr, Ng), dtype=torch.float32, pin_memory=True)
-    for host in (Ah, Bh):  # fill on the GPU (host RNG over 2^30 elements would dominate the run time)
+    # fill on the GPU (host RNG over 2^30 elements would dominate the run time); B is the replicated operand:
+    # every rank must hold the same values, A is this rank's shard
+    for host, seed in ((Ah, 0x5EED0010 + rank), (Bh, 0x5EED0011)):
+        gfill = torch.Generator(device="cuda"); gfill.manual_seed(seed)
         for r0 in range(0, host.shape[0], 4096):
-            host[r0:r0 + 4096].copy_(torch.rand((min(4096, host.shape[0] - r0), host.shape[1]), device="cuda"))
+            host[r0:r0 + 4096].copy_(torch.rand((min(4096, host.shape[0] - r0), host.shape[1]), device="cuda", generator=gfill))
     torch.cuda.synchronize()
     e2e_steps = max(1, min(args.steps, 3))
     from bof_b200 import dist as bdist
