@@ -146,6 +146,8 @@ class Drainer {
 
 namespace {
 
+constexpr int kGemmRing = 4;  // P/C block generations in flight in bof_host_gemm
+
 thread_local std::string g_create_err;
 
 #define BOF_TRY(expr)          \
@@ -170,9 +172,10 @@ enum Slot {
   S_DENSE_T,       // its transposed / split form
   S_BLK0 = 2,      // per-block buffers, two generations each (b = 0/1 added to the slot id)
   S_OFFS = 2, S_IDX64 = 4, S_IDX32 = 6, S_VALS = 8, S_CBLK = 10, S_CBLK_T = 12,
-  S_PRAW = 14, S_PPLANES = 16,
   S_WS = 18,       // kernel workspaces
   S_OUT0 = 19, S_OUT1, S_OUT2, S_MISC,
+  // host gemm: ring of kGemmRing generations (g added to the slot id)
+  S_PRAW = 24, S_PPLANES = 28, S_GCBLK = 32,
 };
 
 cudaEvent_t get_event(bof_ctx* ctx, size_t i) {
@@ -1005,44 +1008,46 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   rb = std::min(rb, round_up<int64_t>(cn.Mo, 256));
   const int nblk = (int)ceil_div<int64_t>(cn.Mo, rb);
   const size_t pb = plane_bytes(rb, kp);
-  float* praw[2]; float* pplanes[2] = {nullptr, nullptr}; float* cblk[2];
-  for (int g = 0; g < 2; ++g) {
+  constexpr int NB = kGemmRing;
+  float* praw[NB]; float* pplanes[NB] = {}; float* cblk[NB];
+  for (int g = 0; g < std::min(NB, nblk); ++g) {
     BOF_TRY(slot_reserve(ctx, S_PRAW + g, (size_t)rb * std::max<int64_t>(K, 1), &praw[g]));
     if (tensor) { void* p; BOF_TRY(slot_reserve(ctx, S_PPLANES + g, 2 * pb, &p)); pplanes[g] = static_cast<float*>(p); }
-    BOF_TRY(slot_reserve(ctx, S_CBLK + g, (size_t)rb * cn.No, &cblk[g]));
+    BOF_TRY(slot_reserve(ctx, S_GCBLK + g, (size_t)rb * cn.No, &cblk[g]));
   }
   auto p_hi_of = [&](int g) { return pplanes[g]; };
   auto p_lo_of = [&](int g) { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pplanes[g]) + pb); };
 
-  // events: 4+g P block uploaded, 6+g P block split, 8+g block computed, 10+g block downloaded, 16+j Q panel
-  bool used[2] = {false, false};
+  // events: 4+g P block uploaded, 8+g P block split, 12+g block computed, 16+g block downloaded, 20+j Q panel
+  constexpr int EV_UP = 4, EV_SPLIT = 8, EV_DONE = 12, EV_DOWN = 16, EV_QPAN = 20;
+  bool used[NB] = {};
   int64_t q_sr = 1, q_sk = 1;  // strides of the raw Q copy on the device
 
   auto upload_block = [&](int i) -> int {  // P rows (+ old C rows when beta != 0) of block i
-    const int g = i & 1;
+    const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, r1 = std::min(cn.Mo, r0 + rb), rows = r1 - r0;
     if (used[g]) {
-      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, (tensor ? 6 : 8) + g), 0));  // raw P of block i-2 consumed
-      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, 10 + g), 0));  // C buffer free
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, (tensor ? EV_SPLIT : EV_DONE) + g), 0));  // raw P of block i-NB consumed
+      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, EV_DOWN + g), 0));       // C buffer free
     }
     int64_t p_sr, p_sk;
     BOF_TRY(upload_rows(cn.psrc, cn.p_sr, cn.p_sk, r0, r1, praw[g], &p_sr, &p_sk, ctx->h2d));
     if (beta != 0.f)
       BOF_TRY(copy2d(ctx, cblk[g], (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
-    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 4 + g), ctx->h2d));
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_UP + g), ctx->h2d));
     return BOF_OK;
   };
   // compute of block i against Q rows [n0, n1) (the whole Q when not panelled); `first`/`last` bracket the block
   auto compute_block = [&](int i, int64_t n0, int64_t n1, bool first, bool last) -> int {
-    const int g = i & 1;
+    const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
     const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;
     if (first) {
-      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 4 + g), 0));
-      if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 10 + g), 0));
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_UP + g), 0));
+      if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_DOWN + g), 0));
       if (tensor) {
         BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi_of(g), p_lo_of(g), kp));
-        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 6 + g), ctx->compute));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_SPLIT + g), ctx->compute));
       }
     }
     if (tensor) {
@@ -1055,17 +1060,17 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
                                beta, cblk[g] + n0, cn.No));
     }
     if (last) {
-      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->compute));
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
       used[g] = true;
     }
     return BOF_OK;
   };
   auto fetch_block = [&](int i) -> int {
-    const int g = i & 1;
+    const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, 8 + g), 0));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_DONE + g), 0));
     BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk[g], (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 10 + g), ctx->d2h));
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
     return BOF_OK;
   };
 
@@ -1076,7 +1081,6 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   const bool q_panels = tensor && !q_on_device && (size_t)cn.No * K * 4 >= (256u << 20);
   const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, 8), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
-  constexpr int EV_QPAN = 16;
   // Every panel is kept as its own tight block at qraw + n0*K: [rows x K] when Q is K-major in the source,
   // [K x rows] (a column range of the stored matrix, pitched copy) when it is not.
   std::vector<int64_t> pan_sr((size_t)n_qpan, 1), pan_sk((size_t)n_qpan, 1);
@@ -1095,36 +1099,35 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, pan_sr[j], pan_sk[j], q_hi + n0 * kp,
                                q_lo + n0 * kp, kp);
   };
-  // Prologue: the first two P blocks ride between the Q panels (h2d order Q0 P0 Q1 P1 Q2 .. Qn) and are
-  // computed against each panel as it lands (compute order follows the arrival order), so the tensor
-  // cores start after one panel + one block of PCIe time and stay fed while the rest of Q uploads.
-  const int npro = std::min(nblk, n_qpan > 1 ? 2 : 1);  // blocks handled by the prologue
+  // Prologue: the first blocks ride between the Q panels (h2d order Q0 P0 Q1 P1 Q2 P2 Q3 P3 Q4 .. Qn) and are
+  // computed against each panel as it lands (compute order = arrival order), so the tensor cores start after
+  // one panel + one block of PCIe time and stay fed while the rest of Q uploads: every new panel unlocks one
+  // tile per prologue block.
+  const int npro = n_qpan > 1 ? std::min({nblk, NB, n_qpan}) : 1;  // blocks handled by the prologue
   auto pan = [&](int j, int64_t* n0, int64_t* n1) { *n0 = (int64_t)j * qpan_rows; *n1 = std::min(cn.No, *n0 + qpan_rows); };
-  BOF_TRY(upload_q_panel(0));
-  BOF_TRY(upload_block(0));
-  if (n_qpan > 1) BOF_TRY(upload_q_panel(1));
-  if (npro > 1) BOF_TRY(upload_block(1));
-  for (int j = 2; j < n_qpan; ++j) BOF_TRY(upload_q_panel(j));
-  for (int j = 0; j < n_qpan; ++j) {
+  for (int t = 0; t < n_qpan; ++t) {
+    BOF_TRY(upload_q_panel(t));
+    if (t < npro) BOF_TRY(upload_block(t));
+  }
+  for (int t = 0; t < n_qpan; ++t) {
     int64_t n0, n1;
-    pan(j, &n0, &n1);
-    BOF_TRY(split_q_panel(j));
-    const bool last = j == n_qpan - 1;
-    BOF_TRY(compute_block(0, n0, n1, j == 0, last));
-    if (npro > 1 && j >= 1) {
-      // block 1 arrived after panel 1: panels 0..1 in one launch, later panels one by one
-      if (j == 1) BOF_TRY(compute_block(1, 0, n1, true, last));
-      else BOF_TRY(compute_block(1, n0, n1, false, last));
+    pan(t, &n0, &n1);
+    BOF_TRY(split_q_panel(t));
+    const bool last = t == n_qpan - 1;
+    for (int i = 0; i < npro; ++i) {
+      if (i == t) BOF_TRY(compute_block(i, 0, n1, true, last));         // block i landed after panel i: panels 0..i at once
+      else if (i < t) BOF_TRY(compute_block(i, n0, n1, false, last));   // then one panel at a time
     }
   }
-  // ---- steady state: stage block i+1 (upload + launch) before fetching block i ----
-  for (int i = 0; i < nblk; ++i) {
-    if (i + 1 < nblk && i + 1 >= npro) {
-      BOF_TRY(upload_block(i + 1));
-      BOF_TRY(compute_block(i + 1, 0, cn.No, true, true));
-    }
-    BOF_TRY(fetch_block(i));
+  // ---- steady state: Q complete; keep NB blocks in flight, fetch the oldest before reusing its buffers ----
+  int next_fetch = 0;
+  for (int i = npro; i < nblk; ++i) {
+    if (next_fetch < i) BOF_TRY(fetch_block(next_fetch++));            // keeps the downloads flowing
+    while (next_fetch <= i - NB) BOF_TRY(fetch_block(next_fetch++));   // block i-NB owned these buffers
+    BOF_TRY(upload_block(i));
+    BOF_TRY(compute_block(i, 0, cn.No, true, true));
   }
+  while (next_fetch < nblk) BOF_TRY(fetch_block(next_fetch++));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
   return BOF_OK;

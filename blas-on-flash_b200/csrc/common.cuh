@@ -55,7 +55,7 @@ struct bof_ctx {
   // Grow-only device buffers owned by the context and reused across host entry points, so that
   // steady-state calls do no cudaMalloc (the reference's counterpart is the Program Cache budget,
   // src/scheduler/cache.cpp).
-  static constexpr int kSlots = 24;
+  static constexpr int kSlots = 40;
   void* slot_ptr[kSlots] = {};
   size_t slot_bytes[kSlots] = {};
   std::vector<cudaEvent_t> events;
