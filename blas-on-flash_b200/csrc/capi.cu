@@ -1009,14 +1009,23 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   const int nblk = (int)ceil_div<int64_t>(cn.Mo, rb);
   const size_t pb = plane_bytes(rb, kp);
   constexpr int NB = kGemmRing;
-  float* praw[NB]; float* pplanes[NB] = {}; float* cblk[NB];
-  for (int g = 0; g < std::min(NB, nblk); ++g) {
+  const int ngen = std::min(NB, nblk);
+  // Ring of block generations.  Planes and C blocks of the ring are each ONE allocation (generation g at
+  // row g*rb), so that consecutive generations can be multiplied in a single launch during the prologue.
+  float* praw[NB];
+  float* hi_all = nullptr; float* lo_all = nullptr; float* c_all = nullptr;
+  for (int g = 0; g < ngen; ++g)
     BOF_TRY(slot_reserve(ctx, S_PRAW + g, (size_t)rb * std::max<int64_t>(K, 1), &praw[g]));
-    if (tensor) { void* p; BOF_TRY(slot_reserve(ctx, S_PPLANES + g, 2 * pb, &p)); pplanes[g] = static_cast<float*>(p); }
-    BOF_TRY(slot_reserve(ctx, S_GCBLK + g, (size_t)rb * cn.No, &cblk[g]));
+  if (tensor) {
+    void* p;
+    BOF_TRY(slot_reserve(ctx, S_PPLANES, 2 * (size_t)ngen * pb, &p));
+    hi_all = static_cast<float*>(p);
+    lo_all = reinterpret_cast<float*>(static_cast<uint8_t*>(p) + (size_t)ngen * pb);
   }
-  auto p_hi_of = [&](int g) { return pplanes[g]; };
-  auto p_lo_of = [&](int g) { return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pplanes[g]) + pb); };
+  BOF_TRY(slot_reserve(ctx, S_GCBLK, (size_t)ngen * rb * cn.No, &c_all));
+  auto p_hi_of = [&](int g) { return hi_all + (size_t)g * rb * kp; };
+  auto p_lo_of = [&](int g) { return lo_all + (size_t)g * rb * kp; };
+  auto cblk_of = [&](int g) { return c_all + (size_t)g * rb * cn.No; };
 
   // events: 4+g P block uploaded, 8+g P block split, 12+g block computed, 16+g block downloaded, 20+j Q panel
   constexpr int EV_UP = 4, EV_SPLIT = 8, EV_DONE = 12, EV_DOWN = 16, EV_QPAN = 20;
@@ -1033,43 +1042,51 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     int64_t p_sr, p_sk;
     BOF_TRY(upload_rows(cn.psrc, cn.p_sr, cn.p_sk, r0, r1, praw[g], &p_sr, &p_sk, ctx->h2d));
     if (beta != 0.f)
-      BOF_TRY(copy2d(ctx, cblk[g], (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
+      BOF_TRY(copy2d(ctx, cblk_of(g), (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_UP + g), ctx->h2d));
     return BOF_OK;
   };
   // compute of block i against Q rows [n0, n1) (the whole Q when not panelled); `first`/`last` bracket the block
-  auto compute_block = [&](int i, int64_t n0, int64_t n1, bool first, bool last) -> int {
+  auto rows_of = [&](int i) { return std::min(cn.Mo, (int64_t)(i + 1) * rb) - (int64_t)i * rb; };
+  // wait for block i's upload (and for its buffers), split its rows into planes
+  auto prepare_block = [&](int i) -> int {
     const int g = i % NB;
-    const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
+    const int64_t rows = rows_of(i);
     const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;
-    if (first) {
-      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_UP + g), 0));
-      if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_DOWN + g), 0));
-      if (tensor) {
-        BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi_of(g), p_lo_of(g), kp));
-        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_SPLIT + g), ctx->compute));
-      }
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_UP + g), 0));
+    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_DOWN + g), 0));
+    if (tensor) {
+      BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi_of(g), p_lo_of(g), kp));
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_SPLIT + g), ctx->compute));
     }
+    return BOF_OK;
+  };
+  // blocks [i0, i0 + cnt) (consecutive generations, no ring wrap) against Q rows [n0, n1), one launch
+  auto gemm_blocks = [&](int i0, int cnt, int64_t n0, int64_t n1) -> int {
+    const int g = i0 % NB;
+    int64_t rows = 0;
+    for (int i = i0; i < i0 + cnt; ++i) rows += rows_of(i);
     if (tensor) {
       GemmEpilogue ep;
-      ep.alpha = alpha; ep.beta = beta; ep.C = cblk[g] + n0; ep.ldc = cn.No;
-      BOF_TRY(launch_gemm_tc(ctx, ctx->compute, cg, rows, n1 - n0, K, kp, p_hi_of(g), p_lo_of(g), q_hi + n0 * kp,
-                             q_lo + n0 * kp, ep, k_chunk_of(ctx)));
-    } else {
-      BOF_TRY(launch_gemm_ffma(ctx, ctx->compute, rows, n1 - n0, K, alpha, praw[g], p_sr, p_sk, qraw + n0 * q_sr, q_sk, q_sr,
-                               beta, cblk[g] + n0, cn.No));
+      ep.alpha = alpha; ep.beta = beta; ep.C = cblk_of(g) + n0; ep.ldc = cn.No;
+      return launch_gemm_tc(ctx, ctx->compute, cg, rows, n1 - n0, K, kp, p_hi_of(g), p_lo_of(g), q_hi + n0 * kp,
+                            q_lo + n0 * kp, ep, k_chunk_of(ctx));
     }
-    if (last) {
-      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
-      used[g] = true;
-    }
+    const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;  // cnt == 1 on this path
+    return launch_gemm_ffma(ctx, ctx->compute, rows, n1 - n0, K, alpha, praw[g], p_sr, p_sk, qraw + n0 * q_sr, q_sk, q_sr,
+                            beta, cblk_of(g) + n0, cn.No);
+  };
+  auto finish_block = [&](int i) -> int {
+    const int g = i % NB;
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
+    used[g] = true;
     return BOF_OK;
   };
   auto fetch_block = [&](int i) -> int {
     const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_DONE + g), 0));
-    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk[g], (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
+    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk_of(g), (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
     return BOF_OK;
   };
@@ -1109,15 +1126,24 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     BOF_TRY(upload_q_panel(t));
     if (t < npro) BOF_TRY(upload_block(t));
   }
+  const bool merge = tensor;  // the CUDA-core path multiplies one block per launch
   for (int t = 0; t < n_qpan; ++t) {
     int64_t n0, n1;
     pan(t, &n0, &n1);
     BOF_TRY(split_q_panel(t));
-    const bool last = t == n_qpan - 1;
-    for (int i = 0; i < npro; ++i) {
-      if (i == t) BOF_TRY(compute_block(i, 0, n1, true, last));         // block i landed after panel i: panels 0..i at once
-      else if (i < t) BOF_TRY(compute_block(i, n0, n1, false, last));   // then one panel at a time
+    // panel t against the blocks that landed before it: one launch over those consecutive generations
+    const int older = std::min(t, npro);
+    if (older > 0) {
+      if (merge) BOF_TRY(gemm_blocks(0, older, n0, n1));
+      else for (int i = 0; i < older; ++i) BOF_TRY(gemm_blocks(i, 1, n0, n1));
     }
+    // block t landed right after panel t: all panels so far at once
+    if (t < npro) {
+      BOF_TRY(prepare_block(t));
+      BOF_TRY(gemm_blocks(t, 1, 0, n1));
+    }
+    if (t == n_qpan - 1)
+      for (int i = 0; i < npro; ++i) BOF_TRY(finish_block(i));
   }
   // ---- steady state: Q complete; keep NB blocks in flight, fetch the oldest before reusing its buffers ----
   int next_fetch = 0;
@@ -1125,7 +1151,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     if (next_fetch < i) BOF_TRY(fetch_block(next_fetch++));            // keeps the downloads flowing
     while (next_fetch <= i - NB) BOF_TRY(fetch_block(next_fetch++));   // block i-NB owned these buffers
     BOF_TRY(upload_block(i));
-    BOF_TRY(compute_block(i, 0, cn.No, true, true));
+    BOF_TRY(prepare_block(i));
+    BOF_TRY(gemm_blocks(i, 1, 0, cn.No));
+    BOF_TRY(finish_block(i));
   }
   while (next_fetch < nblk) BOF_TRY(fetch_block(next_fetch++));
   BOF_TRY(sync_all(ctx));

@@ -126,9 +126,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* full_bar, void* dst,
@@ -472,7 +469,6 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
           mbar_wait(&tail->tmem_full[buf], (acc_iter >> 1) & 1u);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_addr + buf * BLOCK_N + half * EPI_COLS;
-          const bool last = (c == num_chunks - 1);
 #pragma unroll
           for (int g = 0; g < EPI_COLS / 32; ++g) {
             uint32_t v[32];
@@ -518,7 +514,6 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tail->tmem_empty[buf]);
-          (void)last;
         }
         if constexpr (CHUNKED) {
           if constexpr (EPI == EPI_GEMM) {

@@ -71,9 +71,7 @@ spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restric
       c = __ldcs(idx + mine);
       a = __ldcs(vals + mine);
     }
-    const int cnt = (int)min((int64_t)L, end - j);
-    // a == 0 for the padded lanes, so the full-width loop below is safe: it gathers row
-    // idx 0 of B at most L-1 extra times on the last chunk; keep it exact instead:
+    const int cnt = (int)min((int64_t)L, end - j);  // nonzeros of this chunk (uniform inside the row group)
     int t = 0;
     for (; t + U <= cnt; t += U) {
       int32_t cc[U];

@@ -69,8 +69,8 @@ typedef struct bof_config {
  * (no reference counterpart; the reference only logs wall time, drivers/csrmm.cpp:62-65). */
 typedef struct bof_stats {
   double h2d_bytes, d2h_bytes;      /* bytes that crossed PCIe                                  */
-  double h2d_ms, d2h_ms;            /* CUDA-event time of the copies (summed per stream)        */
-  double kernel_ms;                 /* CUDA-event time of the compute kernels                   */
+  double h2d_ms, d2h_ms;            /* reserved (0 in this version)                             */
+  double kernel_ms;                 /* CUDA-event time of the most recent tensor-core GEMM kernel */
   double stage_in_ms, stage_out_ms; /* host memcpy pageable<->pinned (wall, summed over threads)*/
   double total_ms;                  /* wall time of the call                                    */
   int64_t kernel_launches;          /* number of this library's kernels launched                */
