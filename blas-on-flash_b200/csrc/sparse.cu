@@ -126,6 +126,149 @@ spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant for the wide shapes (k a multiple of 128): the block's slice of the A stream --
+// the (col, val) pairs of its 8 consecutive rows, contiguous in CSR -- is brought into shared memory
+// with two 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx) issued by one thread, instead of
+// per-warp register loads + shuffles; the warps then read (col, val) as smem broadcasts and keep U
+// float4 gathers of B rows in flight each.  Slices whose ends are not 16-byte aligned (bulk copies need
+// 16-byte aligned addresses and sizes) are staged with ordinary coalesced loads by the whole block.
+// Slices larger than the staging buffer are walked in chunks.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMM_TMA_CAP = 2048;  // elements per staging chunk: 8 KiB of columns + 8 KiB of values
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+template <int KV, int U>
+__global__ void __launch_bounds__(256, 4)
+spmm_csr_rm_tma_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
+                       const int32_t* __restrict__ idx, const int64_t* __restrict__ offs,
+                       const float* __restrict__ B, int64_t ldb, float beta, float* __restrict__ C,
+                       int64_t ldc) {
+  __shared__ __align__(16) int32_t s_idx[SPMM_TMA_CAP];
+  __shared__ __align__(16) float s_val[SPMM_TMA_CAP];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * 8;
+  const int64_t row = row0 + warp;
+  const int64_t col0 = (int64_t)blockIdx.y * (128 * KV) + 4 * lane;
+  const int64_t base = offs[0];
+  const int64_t seg_beg = offs[row0] - base;
+  const int64_t seg_end = offs[min(row0 + 8, m)] - base;
+  int64_t beg = 0, end = 0;
+  if (row < m) { beg = offs[row] - base; end = offs[row + 1] - base; }
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  bool col_ok[KV];
+  float4 acc[KV];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    col_ok[v] = (col0 + (int64_t)v * 128) < k;
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  uint32_t parity = 0;
+  for (int64_t cs = seg_beg; cs < seg_end; cs += SPMM_TMA_CAP) {
+    const int cnt = (int)min((int64_t)SPMM_TMA_CAP, seg_end - cs);
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(idx + cs) | reinterpret_cast<uintptr_t>(vals + cs)) & 15) == 0 &&
+                         (cnt & 3) == 0;
+    if (bulk_ok) {
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        const uint32_t bar = smem_addr_u32(&s_bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr_u32(s_idx)),
+                     "l"(idx + cs), "r"(bytes), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr_u32(s_val)),
+                     "l"(vals + cs), "r"(bytes), "r"(bar)
+                     : "memory");
+      }
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr_u32(&s_bar)), "r"(parity)
+            : "memory");
+      }
+      parity ^= 1u;
+    } else {
+      for (int i = threadIdx.x; i < cnt; i += 256) {
+        s_idx[i] = __ldcs(idx + cs + i);
+        s_val[i] = __ldcs(vals + cs + i);
+      }
+      __syncthreads();
+    }
+
+    // this warp's row, restricted to the chunk
+    const int64_t jb = max(beg, cs), je = min(end, cs + cnt);
+    int64_t j = jb;
+    for (; j + U <= je; j += U) {
+      int32_t cc[U];
+      float aa[U];
+      float4 bb[U][KV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cc[u] = s_idx[j - cs + u];
+        aa[u] = s_val[j - cs + u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float* brow = B + (int64_t)cc[u] * ldb + col0;
+#pragma unroll
+        for (int v = 0; v < KV; ++v)
+          bb[u][v] = col_ok[v] ? ldg_f4(brow + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < KV; ++v) fma4(acc[v], aa[u], bb[u][v]);
+    }
+    for (; j < je; ++j) {
+      const int32_t cc = s_idx[j - cs];
+      const float aa = s_val[j - cs];
+      const float* brow = B + (int64_t)cc * ldb + col0;
+#pragma unroll
+      for (int v = 0; v < KV; ++v)
+        if (col_ok[v]) fma4(acc[v], aa, ldg_f4(brow + v * 128));
+    }
+    __syncthreads();  // everyone is done with the staging buffers before the next chunk overwrites them
+  }
+
+  if (row >= m) return;
+  float* crow = C + row * ldc + col0;
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    if (!col_ok[v]) continue;
+    float4 r;
+    r.x = alpha * acc[v].x;
+    r.y = alpha * acc[v].y;
+    r.z = alpha * acc[v].z;
+    r.w = alpha * acc[v].w;
+    float4* dst = reinterpret_cast<float4*>(crow + v * 128);
+    if (beta != 0.f) {
+      const float4 old = *dst;
+      r.x = fmaf(beta, old.x, r.x);
+      r.y = fmaf(beta, old.y, r.y);
+      r.z = fmaf(beta, old.z, r.z);
+      r.w = fmaf(beta, old.w, r.w);
+    }
+    __stcs(dst, r);
+  }
+}
+
 // Any k, any alignment: a warp owns a row and strides over the columns.
 __global__ void __launch_bounds__(256)
 spmm_csr_rm_generic_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
@@ -273,6 +416,16 @@ transpose_kernel(int64_t rows, int64_t cols, float alpha, const float* __restric
   }
 }
 
+template <int KV, int U>
+int spmm_tma_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha, const float* vals,
+                    const int32_t* idx, const int64_t* offs, const float* B, int64_t ldb, float beta, float* C,
+                    int64_t ldc) {
+  dim3 grid((unsigned)ceil_div<int64_t>(m, 8), (unsigned)ceil_div<int64_t>(k, 128 * KV));
+  spmm_csr_rm_tma_kernel<KV, U><<<grid, 256, 0, s>>>(m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+  BOF_LAUNCH_CHECK(ctx, "spmm_csr_rm_tma_kernel");
+  return BOF_OK;
+}
+
 template <int L, int KV, int U = 4, int MINB = 4>
 int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                     const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
@@ -311,6 +464,12 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
   static const int variant = getenv("BOF_SPMM_VARIANT") ? atoi(getenv("BOF_SPMM_VARIANT")) : -1;
 #define BOF_SPMM_V(L, KV, U, MINB) \
   return spmm_vec_launch<L, KV, U, MINB>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
+  if (variant == 6 && k > 64)  // TMA-staged A stream
+    return (k <= 128) ? spmm_tma_launch<1, 8>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
+                      : spmm_tma_launch<2, 4>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+  if (variant == 7 && k > 64)
+    return (k <= 128) ? spmm_tma_launch<1, 4>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
+                      : spmm_tma_launch<2, 8>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
   if (k <= 128) {
     switch (variant) {
       case 1: BOF_SPMM_V(32, 1, 4, 5);

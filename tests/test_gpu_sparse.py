@@ -168,3 +168,13 @@ def test_host_csrmm_empty(ctx):
     ia = np.zeros(1, np.int64)
     e = np.zeros(0, np.float32)
     ctx.host_csrmm("N", 0, 5, 3, 1.0, 0.0, e, ia, np.zeros(0, np.int64), "R", np.zeros((5, 3), np.float32), e)
+
+
+@pytest.mark.parametrize("variant", ["6", "3"])
+def test_spmm_kernel_variants_child_process(variant):
+    """BOF_SPMM_VARIANT=6 selects the TMA-staged A-stream kernel (cp.async.bulk + mbarrier); 3 is a register variant."""
+    import os, subprocess, sys
+    script = Path(__file__).parent / "spmm_variant_check.py"
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, BOF_SPMM_VARIANT=variant),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SPMM_VARIANT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

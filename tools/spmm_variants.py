@@ -20,7 +20,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         del vals, idx, offs, B, C
     print(json.dumps(out), flush=True)
 else:
-    for v in range(6):
+    for v in range(8):
         env = dict(os.environ, BOF_SPMM_VARIANT=str(v))
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)
