@@ -57,16 +57,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in a thread every 10 ms (an nvidia-smi child
+    takes longer to start than a short multi-GPU timed region lasts), nvidia-smi -lms as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, pci_bus_id: str = None):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.thread, self.run = None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = None
+            for bus in ((pci_bus_id, pci_bus_id.encode()) if pci_bus_id else ()):
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+                    break
+                except Exception:
+                    continue
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while self.run:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((sm, self.max_sm, mask))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -80,24 +119,42 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        if self.nvml:
+            self.run = False
+            self.thread.join(timeout=1)
+            for s_, m_, mask in self.rows:
+                sm.append(s_); mx.append(m_)
+                reasons.update(k for k, bit in self.BITS.items() if mask & bit)
+            src = "nvml"
+        else:
+            if self.proc:
+                self.proc.terminate()
+                try:
+                    self.proc.wait(timeout=2)
+                except Exception:
+                    self.proc.kill()
+            for r in self.rows:
+                try:
+                    sm.append(float(r[0])); mx.append(float(r[1]))
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            src = "nvidia-smi"
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": src}
+
+
+def gpu_pci_bus_id(torch, local: int):
+    """NVML's index ignores CUDA_VISIBLE_DEVICES; address the device torch uses by its PCI bus id."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        return "%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except Exception:
+        return None
 
 
 def cpu_gemm_sample(reps: int = 2):
@@ -268,7 +325,7 @@ def main():
     for _ in range(args.warmup):
         ctx.sgemm("R", "N", "N", Mr, Ng, Kg, 1.0, A, 0, B, 0, 0.0, Cd, 0, ws=ws)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local, gpu_pci_bus_id(torch, local)); sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     kern_ms = []
@@ -293,7 +350,7 @@ def main():
     # per useful flop the kernel issues one TF32 MMA flop (hi*hi) and two BF16 MMA flops (the cross terms)
     peak = 1.0 / (1.0 / tf32_peak + 2.0 / bf16_peak)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if world == 1 and Mg == 32768 else None,
                 "kernel": "gemm3xtf32_kernel<2,EPI_GEMM,chunked,hybrid>", "kernel_ms": t_kernel * 1e3,
                 "peak_note": "useful fp32 flops (2mnk) per launch against 1/(1/TF32 + 2/BF16): one tf32 MMA (hi*hi) and two "
                              f"bf16 MMAs (cross terms) per product; BF16 = MEASURED_PEAKS.json ({pk['src']}) "

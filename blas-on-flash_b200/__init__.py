@@ -15,7 +15,7 @@ import ctypes as C
 from . import _capi
 from ._capi import BofConfig, BofError, BofStats, ch, load, ptr
 
-__all__ = ["Context", "KMeans", "BofError", "BofStats", "load"]
+__all__ = ["Context", "KMeans", "ResidentCsr", "BofError", "BofStats", "load"]
 
 
 def _cur_stream() -> int:
@@ -189,4 +189,35 @@ class KMeans:
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.bof_kmeans_close(self.h)
+            self.h = None
+
+
+class ResidentCsr:
+    """A kept in HBM across csrmm / csrgemv calls (bof_csr_*; the eigensolver inner loop of SURVEY 8(f)-2)."""
+
+    def __init__(self, ctx: Context, m, n, a, ia, ja):
+        self.ctx, self.m, self.n = ctx, m, n
+        h = C.c_void_p()
+        ctx._check(ctx.lib.bof_csr_open(ctx.h, m, n, ptr(a), ptr(ia), ptr(ja), C.byref(h)))
+        self.h = h
+
+    def build_transpose(self):
+        self.ctx._check(self.ctx.lib.bof_csr_build_transpose(self.h))
+
+    def arrays(self, trans_a="N"):
+        """(vals, idx, offs) device addresses and nnz of A ('N') or A^T ('T')."""
+        v, i, o, z = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self.ctx._check(self.ctx.lib.bof_csr_arrays(self.h, ch(trans_a), C.byref(v), C.byref(i), C.byref(o),
+                                                    C.byref(z)))
+        return v.value, i.value, o.value, z.value
+
+    def mm(self, trans_a, k, alpha, beta, ord_b, b, c):
+        self.ctx._check(self.ctx.lib.bof_csr_mm(self.h, ch(trans_a), k, alpha, beta, ch(ord_b), ptr(b), ptr(c)))
+
+    def mv(self, trans_a, x, y):
+        self.ctx._check(self.ctx.lib.bof_csr_mv(self.h, ch(trans_a), ptr(x), ptr(y)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.bof_csr_close(self.h)
             self.h = None

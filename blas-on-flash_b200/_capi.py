@@ -83,6 +83,12 @@ PROTOTYPES = {
     "bof_host_csrmm_devb": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "bof_host_csrgemv": (C.c_int, [_vp, _ch, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "bof_host_csrcsc": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bof_csr_open": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "bof_csr_build_transpose": (C.c_int, [_vp]),
+    "bof_csr_arrays": (C.c_int, [_vp, _ch, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "bof_csr_mm": (C.c_int, [_vp, _ch, _i64, _f32, _f32, _ch, _vp, _vp]),
+    "bof_csr_mv": (C.c_int, [_vp, _ch, _vp, _vp]),
+    "bof_csr_close": (C.c_int, [_vp]),
     "bof_kmeans_open": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, C.POINTER(_vp)]),
     "bof_kmeans_local_step": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "bof_kmeans_update": (C.c_int, [_vp]),

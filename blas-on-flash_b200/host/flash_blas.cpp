@@ -3,6 +3,7 @@
 // and calls the matching bof_host_* pipeline; nothing here computes.
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -22,6 +23,18 @@ int env_device() {
   for (const char* name : {"BOF_DEVICE", "LOCAL_RANK"})
     if (const char* v = std::getenv(name)) return std::atoi(v);
   return 0;
+}
+
+// matrices pinned in HBM by csr_pin, keyed by the address of their value array
+struct Pinned { bof_csr* h; FBLAS_UINT m, n; const void *ia, *ja; };
+std::map<const void*, Pinned> g_pinned;
+
+bof_csr* find_pinned(flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja, FBLAS_UINT m, FBLAS_UINT n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_pinned.find(a.ptr);
+  if (it == g_pinned.end()) return nullptr;
+  const Pinned& p = it->second;
+  return (p.m == m && p.n == n && p.ia == ia.ptr && p.ja == ja.ptr) ? p.h : nullptr;
 }
 
 FBLAS_INT done(const char* what, int rc) {
@@ -52,6 +65,8 @@ void flash_setup(std::string mntdir) {
 
 void flash_destroy() {
   std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_pinned) bof_csr_close(kv.second.h);
+  g_pinned.clear();
   if (g_ctx) bof_ctx_destroy(g_ctx);
   g_ctx = nullptr;
 }
@@ -94,6 +109,8 @@ FBLAS_INT csrmm(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE a
                 flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja, CHAR ord_b, FPTYPE* b, FPTYPE* c) {
   bof_ctx* ctx = flash_context();
   if (!ctx) return -1;
+  if (bof_csr* h = find_pinned(a, ia, ja, m, n))
+    return done("csrmm", bof_csr_mm(h, trans_a, (int64_t)k, alpha, beta, ord_b, b, c));
   return done("csrmm", bof_host_csrmm(ctx, trans_a, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta, a.ptr,
                                       reinterpret_cast<const int64_t*>(ia.ptr),
                                       reinterpret_cast<const int64_t*>(ja.ptr), ord_b, b, c));
@@ -113,9 +130,37 @@ FBLAS_INT csrgemv(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, flash_ptr<FPTYPE> a,
                   flash_ptr<MKL_INT> ja, FPTYPE* b, FPTYPE* c) {
   bof_ctx* ctx = flash_context();
   if (!ctx) return -1;
+  if (bof_csr* h = find_pinned(a, ia, ja, m, n)) return done("csrgemv", bof_csr_mv(h, trans_a, b, c));
   return done("csrgemv", bof_host_csrgemv(ctx, trans_a, (int64_t)m, (int64_t)n, a.ptr,
                                           reinterpret_cast<const int64_t*>(ia.ptr),
                                           reinterpret_cast<const int64_t*>(ja.ptr), b, c));
+}
+
+FBLAS_INT csr_pin(FBLAS_UINT m, FBLAS_UINT n, flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja,
+                  bool with_transpose) {
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  csr_unpin(a);
+  bof_csr* h = nullptr;
+  int rc = bof_csr_open(ctx, (int64_t)m, (int64_t)n, a.ptr, reinterpret_cast<const int64_t*>(ia.ptr),
+                        reinterpret_cast<const int64_t*>(ja.ptr), &h);
+  if (rc == 0 && with_transpose) rc = bof_csr_build_transpose(h);
+  if (rc != 0) {
+    if (h) bof_csr_close(h);
+    return done("csr_pin", rc);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_pinned[a.ptr] = Pinned{h, m, n, ia.ptr, ja.ptr};
+  return 0;
+}
+
+FBLAS_INT csr_unpin(flash_ptr<FPTYPE> a) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_pinned.find(a.ptr);
+  if (it == g_pinned.end()) return 0;
+  bof_csr_close(it->second.h);
+  g_pinned.erase(it);
+  return 0;
 }
 
 FBLAS_INT kmeans_lloyd(flash_ptr<FPTYPE> points, flash_ptr<FPTYPE> centers, FBLAS_UINT npoints, FBLAS_UINT ndims,

@@ -215,6 +215,28 @@ int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const flo
 int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const int64_t* ja,
                     const float* a, int64_t* ia_tr, int64_t* ja_tr, float* a_tr);
 
+/* A resident in HBM across calls: the in-memory-B/C csrmm overload and csrgemv as the inner
+ * loop of an eigensolver re-multiply the same A (include/flash_blas.h:43-46; src/blas/csrmm.cpp:453-472;
+ * drivers/csrmm_pmem.cpp).  The reference re-reads A from flash every call because its Cache
+ * (include/scheduler/cache.h:11-42) is flushed when a kernel returns; here bof_csr_open uploads A once
+ * (host arrays as flash_ptr::ptr gives them; indices narrowed to int32 on the device) and bof_csr_mm /
+ * bof_csr_mv take host B, C / x, y with the argument meaning of bof_host_csrmm / bof_host_csrgemv.
+ * trans_a = 'T' products run on a resident copy of A^T (stable csr2csc, built on first use or by
+ * bof_csr_build_transpose; it doubles the footprint); bof_csr_mv('T') without that copy uses the scatter
+ * kernel on A.  bof_csr_arrays exposes the device arrays (int32 indices, int64 offsets) of A or A^T for
+ * callers that keep B and C on the device and call bof_spmm_csr_f32 / bof_spmv_csr_f32 themselves.
+ * One call at a time per context, like every other entry point. */
+typedef struct bof_csr bof_csr;
+int bof_csr_open(bof_ctx* ctx, int64_t m, int64_t n, const float* a, const int64_t* ia, const int64_t* ja,
+                 bof_csr** out);
+int bof_csr_build_transpose(bof_csr* h);
+int bof_csr_arrays(bof_csr* h, char trans_a, const float** vals, const int32_t** idx, const int64_t** offs,
+                   int64_t* nnz);
+int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, char ord_b, const float* b,
+               float* c);
+int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y);
+int bof_csr_close(bof_csr* h);
+
 /* One Lloyd iteration on this rank's shard of the points, device-resident across calls:
  * bof_kmeans_open uploads the shard once (drivers/kmeans.cpp:206-217: points mapped, norms
  * computed once); bof_kmeans_local_step = closest_centers + per-cluster partial sums

@@ -61,6 +61,16 @@ FBLAS_INT csrgemv(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n,
                   flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja,
                   FPTYPE* b, FPTYPE* c);
 
+// ---- extension: keep a CSR matrix in HBM across calls ------------------------------------------
+// Iterative callers (the block Krylov-Schur eigensolver of the paper, drivers/csrmm_pmem.cpp) multiply by the same
+// A many times; the reference re-reads it from flash each call.  After csr_pin(m, n, a, ia, ja) every
+// flash::csrmm / flash::csrgemv whose (a, ia, ja, m, n) match runs on the HBM-resident copy and moves only the
+// dense operands.  The files behind a, ia, ja must not change while pinned.  with_transpose also keeps A^T
+// (needed by trans_a = 'T' products; built on first use otherwise).  flash_destroy() unpins everything.
+FBLAS_INT csr_pin(FBLAS_UINT m, FBLAS_UINT n, flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_INT> ja,
+                  bool with_transpose = false);
+FBLAS_INT csr_unpin(flash_ptr<FPTYPE> a);
+
 // ---- extension: the Lloyd loop that lives in the reference's drivers ---------------------------
 // `n_iters` iterations of drivers/kmeans.cpp:103-189 (closest_centers + centroid update) with the
 // points resident in HBM: fused distance-GEMM/argmin, deterministic centroid reduce.  `centers` is

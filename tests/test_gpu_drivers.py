@@ -100,3 +100,21 @@ def test_kmeans_driver_one_iteration(tmp_path):
         assert oracle.rel_fro(got, ref_c) <= TOL
     else:  # a near-tie may move one point between clusters; centroids still agree closely
         assert oracle.rel_fro(got, ref_c) <= 1e-3
+
+
+@pytest.mark.parametrize("trans,n_calls", [("N", 1), ("N", 3), ("T", 2)])
+def test_csrmm_pmem_driver(tmp_path, trans, n_calls):
+    """drivers/csrmm_pmem.cpp: B, C in host memory (flash_blas.h:43-46); n_calls > 1 pins A in HBM (flash::csr_pin)."""
+    rng = np.random.default_rng(12)
+    m, n, k = 2100, 1700, 160
+    a, ia, ja = ragged_csr(rng, m, n, 35)
+    fa, fj, fi = write_csr(tmp_path, a, ia, ja)
+    rows_b, rows_c = (n, m) if trans == "N" else (m, n)
+    B = rng.random((rows_b, k), dtype=np.float32); C0 = rng.random((rows_c, k), dtype=np.float32)
+    B.tofile(tmp_path / "B.bin"); C0.tofile(tmp_path / "C.bin")
+    args = [fa, fj, fi, tmp_path / "B.bin", tmp_path / "C.bin", m, n, k, 1.25, 0.5, trans, "R"]
+    out = run("csrmm_pmem", *args, *([n_calls] if n_calls > 1 else []))
+    assert out.count("returned 0") == n_calls + (1 if n_calls > 1 else 0)
+    got = np.fromfile(tmp_path / "C.bin", dtype=np.float32).reshape(rows_c, k)
+    ref = oracle.csrmm(trans, m, n, k, 1.25, 0.5, a, ia, ja, "R", B, C0, acc64=True)
+    assert oracle.rel_fro(got, ref) <= TOL
