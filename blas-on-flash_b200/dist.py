@@ -80,3 +80,26 @@ def allgather_dense(host_full, out_dev, group=None):
                 dist.broadcast(out_dev[s0:s1], src=src, group=group)
     torch.cuda.current_stream().synchronize()  # the library's streams do not know about this one
     return (r1 - r0) * host_full[0].numel() * host_full.element_size()
+
+
+def sum_partials_fixed_order(y_local, group=None):
+    """csrgemv 'T' over row shards (SURVEY 8(e)): every rank holds a full-length partial y = A_shard^T x_shard;
+    the result is their sum taken on the host in rank order, so it is bitwise reproducible and identical on
+    every rank (the reference adds task results in completion order under a mutex,
+    include/tasks/csrgemv_task.h:170-176).  The partials travel with all_gather (exact copies), not a reduction."""
+    import torch
+    import torch.distributed as dist
+
+    y_local = np.ascontiguousarray(y_local, dtype=np.float32)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return y_local.copy()
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(y_local)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    out = parts[0].cpu().numpy().copy()
+    for p in parts[1:]:
+        out += p.cpu().numpy()
+    return out

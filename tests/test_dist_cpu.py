@@ -40,6 +40,17 @@ def _worker(rank, world, port, q):
         ok_spmm = np.array_equal(mine, full[r0:r1])
         spans = [None] * world
         dist.all_gather_object(spans, (r0, r1, int(z1 - z0)))
+        # ---- csrgemv: 'N' shards are disjoint rows; 'T' partials summed on the host in rank order ----
+        x_n = rng.random(n, dtype=np.float32); x_t = rng.random(m, dtype=np.float32)
+        y_n = oracle.csrgemv("N", r1 - r0, n, a[z0:z1], ia[r0:r1 + 1], ja[z0:z1], x_n)
+        ok_gemv = np.array_equal(y_n, oracle.csrgemv("N", m, n, a, ia, ja, x_n)[r0:r1])
+        part = oracle.csrgemv("T", r1 - r0, n, a[z0:z1], ia[r0:r1 + 1], ja[z0:z1], x_t[r0:r1])
+        y_t = bdist.sum_partials_fixed_order(part)
+        ok_gemv = ok_gemv and oracle.rel_fro(y_t, oracle.csrgemv("T", m, n, a, ia, ja, x_t, acc64=True)) < 1e-5
+        sums_t = [None] * world
+        dist.all_gather_object(sums_t, y_t.tobytes())
+        ok_gemv = ok_gemv and all(b == sums_t[0] for b in sums_t)  # bitwise identical on every rank
+        ok_spmm = ok_spmm and ok_gemv
         # ---- gemm: equal row shards ----
         g0, g1 = bdist.row_shard(37, world, rank)
         # ---- kmeans: local sums/counts -> allreduce -> divide == single-process update ----
