@@ -201,12 +201,17 @@ int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
   if (!ring.empty()) return BOF_OK;
   ring.resize((size_t)ctx->cfg.n_stage_bufs);
   for (auto& sl : ring) {
-    if (cudaMallocHost(&sl.ptr, ctx->cfg.stage_bytes) != cudaSuccess) {
+    if (cudaMallocHost(&sl.ptr, ctx->cfg.stage_bytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
+      for (auto& u : ring) {  // a half-built ring must not be mistaken for a usable one by the next call
+        if (u.ptr) cudaFreeHost(u.ptr);
+        if (u.ev) cudaEventDestroy(u.ev);
+      }
+      ring.clear();
       return fail(ctx, BOF_ENOMEM, "cudaMallocHost of a %llu-byte staging buffer failed",
                   (unsigned long long)ctx->cfg.stage_bytes);
     }
-    BOF_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
   }
   if (!ctx->pool) ctx->pool = new CopyPool(ctx->cfg.n_copy_threads);
   if (!ctx->pool_out) ctx->pool_out = new CopyPool(ctx->cfg.n_copy_threads);
@@ -384,6 +389,27 @@ int sync_all(bof_ctx* ctx) {
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
   return drain_wait(ctx);
 }
+
+// After a failed call nothing of it may still be running: queued copies and the drainer thread reference the
+// caller's host buffers and the context's slots.  Keeps the recorded error message.
+void quiesce(bof_ctx* ctx) {
+  cudaStreamSynchronize(ctx->h2d);
+  cudaStreamSynchronize(ctx->compute);
+  cudaStreamSynchronize(ctx->d2h);
+  if (ctx->drainer) ctx->drainer->wait_idle();
+  for (auto* ring : {&ctx->stage_in, &ctx->stage_out})
+    for (auto& sl : *ring) sl.in_flight = false;
+  cudaGetLastError();
+}
+
+// Every host entry point holds one: any return that did not set `ok` leaves the context quiescent.
+struct CallGuard {
+  bof_ctx* ctx;
+  bool ok = false;
+  explicit CallGuard(bof_ctx* c) : ctx(c) {}
+  ~CallGuard() { if (!ok && ctx) quiesce(ctx); }
+  int done() { ok = true; return BOF_OK; }
+};
 
 
 // Canonical form of a GEMM: Cout[Mo x No] (row-major, ldc) = P[Mo x K] * Q[No x K]^T where
@@ -781,9 +807,10 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   BOF_REQUIRE(ctx, m >= 0 && n >= 0 && k >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrmm: bad dimension");
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   const int64_t out_rows = trans_a == 'N' ? m : n;   // rows of C
   const int64_t in_rows = trans_a == 'N' ? n : m;    // rows of B
-  if (out_rows == 0 || k == 0) { stats_end(ctx); return BOF_OK; }
+  if (out_rows == 0 || k == 0) { stats_end(ctx); return call_guard.done(); }
   const bool colmaj = ord_b == 'C';
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
 
@@ -869,7 +896,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     BOF_TRY(copy1d(ctx, c, Cio, (size_t)out_rows * k * 4, D2H, ctx->compute));
     BOF_TRY(sync_all(ctx));
     stats_end(ctx);
-    return BOF_OK;
+    return call_guard.done();
   }
 
   // ---- 'N': streamed row blocks ----
@@ -943,7 +970,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   }
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
@@ -971,7 +998,8 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   BOF_REQUIRE(ctx, !q_on_device || ord == 'R', "gemm: a device-resident B is supported for mat_ord='R' only");
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
-  if (cn.Mo == 0 || cn.No == 0) { stats_end(ctx); return BOF_OK; }
+  CallGuard call_guard(ctx);
+  if (cn.Mo == 0 || cn.No == 0) { stats_end(ctx); return call_guard.done(); }
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
   const int path = pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
   const int64_t K = cn.K, kp = padded_k(K);
@@ -1159,7 +1187,7 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   while (next_fetch < nblk) BOF_TRY(fetch_block(next_fetch++));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
@@ -1181,10 +1209,11 @@ int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const flo
   BOF_REQUIRE(ctx, m >= 0 && n >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrgemv: bad dimension");
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
   const bool tr = trans_a == 'T';
   const int64_t xlen = tr ? m : n, ylen = tr ? n : m;
-  if (ylen == 0) { stats_end(ctx); return BOF_OK; }
+  if (ylen == 0) { stats_end(ctx); return call_guard.done(); }
   float *xd, *yd;
   BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)std::max<int64_t>(xlen, 1), &xd));
   BOF_TRY(slot_reserve(ctx, S_CBLK, (size_t)ylen, &yd));
@@ -1235,7 +1264,7 @@ int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const flo
   BOF_TRY(copy1d(ctx, c, yd, (size_t)ylen * 4, D2H, ctx->compute));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 // flash::csrcsc: the whole matrix is transposed in HBM in one shot (the reference's two-phase
@@ -1246,6 +1275,7 @@ int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const
   BOF_REQUIRE(ctx, m >= 0 && n >= 0 && m < (1ll << 31) && n < (1ll << 31), "csrcsc: bad dimension");
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
   const int64_t nnz = ia[m] - ia[0];
   BOF_REQUIRE(ctx, nnz >= 0 && nnz < (1ll << 31), "csrcsc: nnz must be in [0, 2^31)");
@@ -1282,7 +1312,7 @@ int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const
   BOF_TRY(copy1d(ctx, ia_tr, offs_t, (size_t)(n + 1) * 8, D2H, ctx->compute));  // offsets last, as csrcsc.cpp:150
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 // ---- resident CSR: A stays in HBM across calls -----------------------------------
@@ -1335,9 +1365,10 @@ int bof_csr_open(bof_ctx* ctx, int64_t m, int64_t n, const float* a, const int64
   BOF_REQUIRE(ctx, nnz >= 0 && nnz < (1ll << 31), "csr_open: nnz must be in [0, 2^31)");
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   bof_csr* h = new bof_csr();
   h->ctx = ctx; h->m = m; h->n = n; h->nnz = nnz;
-  auto guard = [&](int rc) { if (rc != BOF_OK) csr_free(h); return rc; };
+  auto guard = [&](int rc) { if (rc != BOF_OK) { quiesce(ctx); csr_free(h); } return rc; };
   if (int rc = guard(csr_alloc(ctx, h, 0, m))) return rc;
   h->offs_host[0].assign(ia, ia + m + 1);
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
@@ -1365,7 +1396,7 @@ int bof_csr_open(bof_ctx* ctx, int64_t m, int64_t n, const float* a, const int64
   if (int rc = guard(sync_all(ctx))) return rc;
   stats_end(ctx);
   *out = h;
-  return BOF_OK;
+  return call_guard.done();
 }
 
 int bof_csr_build_transpose(bof_csr* h) {
@@ -1373,6 +1404,7 @@ int bof_csr_build_transpose(bof_csr* h) {
   if (h->have_t) return BOF_OK;
   bof_ctx* ctx = h->ctx;
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  CallGuard call_guard(ctx);
   BOF_TRY(csr_alloc(ctx, h, 1, h->n));
   void* ws;
   const size_t wsb = csr2csc_workspace_bytes(h->m, h->n, h->nnz);
@@ -1383,7 +1415,7 @@ int bof_csr_build_transpose(bof_csr* h) {
   BOF_TRY(copy1d(ctx, h->offs_host[1].data(), h->offs[1], (size_t)(h->n + 1) * 8, cudaMemcpyDeviceToHost, ctx->compute));
   BOF_TRY(sync_all(ctx));
   h->have_t = true;
-  return BOF_OK;
+  return call_guard.done();
 }
 
 int bof_csr_arrays(bof_csr* h, char trans_a, const float** vals, const int32_t** idx, const int64_t** offs,
@@ -1412,8 +1444,9 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
   const int t = trans_a == 'T';
   if (t) BOF_TRY(bof_csr_build_transpose(h));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   const int64_t out_rows = t ? h->n : h->m, in_rows = t ? h->m : h->n;
-  if (out_rows == 0 || k == 0) { stats_end(ctx); return BOF_OK; }
+  if (out_rows == 0 || k == 0) { stats_end(ctx); return call_guard.done(); }
   const bool colmaj = ord_b == 'C';
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
   const float* vals = h->vals[t];
@@ -1520,7 +1553,7 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
   if (prev_p >= 0) BOF_TRY(fetch_block(prev_p, prev_i, prev_g));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 // y = op(A) x with host x, y.  'T' uses the resident A^T when it has been built (a deterministic gather SpMV),
@@ -1531,9 +1564,10 @@ int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y) {
   BOF_REQUIRE(ctx, is_nt(trans_a), "csrgemv trans_a error : expected=N or T, found=%c", trans_a);
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
+  CallGuard call_guard(ctx);
   const bool tr = trans_a == 'T';
   const int64_t xlen = tr ? h->m : h->n, ylen = tr ? h->n : h->m;
-  if (ylen == 0) { stats_end(ctx); return BOF_OK; }
+  if (ylen == 0) { stats_end(ctx); return call_guard.done(); }
   float *xd, *yd;
   BOF_TRY(slot_reserve(ctx, S_MISC, (size_t)std::max<int64_t>(xlen, 1), &xd));
   BOF_TRY(slot_reserve(ctx, S_OUT0, (size_t)ylen, &yd));
@@ -1545,7 +1579,7 @@ int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y) {
   BOF_TRY(copy1d(ctx, y, yd, (size_t)ylen * 4, cudaMemcpyDeviceToHost, s));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);
-  return BOF_OK;
+  return call_guard.done();
 }
 
 int bof_csr_close(bof_csr* h) {
@@ -1606,7 +1640,7 @@ int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim
     }
   }
   cudaStream_t s = ctx->compute;
-  auto guard = [&](int rc) { if (rc != BOF_OK) kmeans_free(km); return rc; };
+  auto guard = [&](int rc) { if (rc != BOF_OK) { quiesce(ctx); kmeans_free(km); } return rc; };
   if (int rc = guard(copy1d(ctx, km->points, points_host, (size_t)npoints * dim * 4, cudaMemcpyHostToDevice, s))) return rc;
   if (int rc = guard(copy1d(ctx, km->centers, centers_host, (size_t)ncenters * dim * 4, cudaMemcpyHostToDevice, s))) return rc;
   if (int rc = guard(launch_row_sqnorm(ctx, s, npoints, dim, km->points, dim, km->p_l2sq))) return rc;
@@ -1640,13 +1674,15 @@ int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host) {
   if (!km) return BOF_EINVAL;
   bof_ctx* ctx = km->ctx;
   cudaStream_t s = ctx->compute;
+  CallGuard call_guard(ctx);
   if (centers_host) BOF_TRY(copy1d(ctx, centers_host, km->centers, (size_t)km->ncenters * km->dim * 4, cudaMemcpyDeviceToHost, s));
   if (assign_host && km->npoints > 0) {
     BOF_TRY(launch_idx_widen(ctx, s, km->assign, km->assign64, km->npoints));
     BOF_TRY(copy1d(ctx, assign_host, km->assign64, (size_t)km->npoints * 8, cudaMemcpyDeviceToHost, s));
   }
   BOF_CUDA(ctx, cudaStreamSynchronize(s));
-  return drain_wait(ctx);
+  BOF_TRY(drain_wait(ctx));
+  return call_guard.done();
 }
 
 void* bof_kmeans_stream(bof_kmeans* km) { return km ? (void*)km->ctx->compute : nullptr; }
