@@ -155,6 +155,10 @@ class Context:
     def host_csrgemv(self, trans_a, m, n, a, ia, ja, b, c):
         self._check(self.lib.bof_host_csrgemv(self.h, ch(trans_a), m, n, ptr(a), ptr(ia), ptr(ja), ptr(b), ptr(c)))
 
+    def host_kmeans_dist(self, ord_, ta, tb, m, n, k, alpha, beta, a, b, c, c_l2sq, p_l2sq, lda=0, ldb=0, ldc=0):
+        self._check(self.lib.bof_host_kmeans_dist(self.h, ch(ord_), ch(ta), ch(tb), m, n, k, alpha, beta, ptr(a), ptr(b),
+                                                  ptr(c), lda, ldb, ldc, ptr(c_l2sq), ptr(p_l2sq)))
+
     def host_csrcsc(self, m, n, ia, ja, a, ia_tr, ja_tr, a_tr):
         self._check(self.lib.bof_host_csrcsc(self.h, m, n, ptr(ia), ptr(ja), ptr(a), ptr(ia_tr), ptr(ja_tr),
                                              ptr(a_tr)))

@@ -81,6 +81,8 @@ PROTOTYPES = {
                                 _i64]),
     "bof_host_gemm_devb": (C.c_int, [_vp, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64, _i64]),
     "bof_host_csrmm_devb": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "bof_host_kmeans_dist": (C.c_int, [_vp, _ch, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64, _i64,
+                                       _vp, _vp]),
     "bof_host_csrgemv": (C.c_int, [_vp, _ch, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "bof_host_csrcsc": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bof_csr_open": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(_vp)]),

@@ -991,7 +991,7 @@ int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alp
 // on the device, so each C block crosses PCIe once.
 static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
                           float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc,
-                          bool q_on_device) {
+                          bool q_on_device, const float* term_m = nullptr, const float* term_n = nullptr) {
   if (!ctx) return BOF_EINVAL;
   Canon cn;
   BOF_TRY(canon_gemm(ctx, ord, ta, tb, m, n, k, a, lda, b, ldb, ldc, &cn));
@@ -1056,6 +1056,23 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   auto p_lo_of = [&](int g) { return lo_all + (size_t)g * rb * kp; };
   auto cblk_of = [&](int g) { return c_all + (size_t)g * rb * cn.No; };
 
+  // flash::kmeans: C(i, j) += term_m[i], then += term_n[j] (i over m, j over n), applied to each block on the
+  // device before it is downloaded.  In canonical (row-major output) form the rows are m for 'R', n for 'C'.
+  float* term_rows_d = nullptr;
+  float* term_cols_d = nullptr;
+  const bool with_terms = term_m != nullptr && term_n != nullptr;
+  const bool canon_rows_are_m = ord == 'R';
+  if (with_terms) {
+    float* t;
+    BOF_TRY(slot_reserve(ctx, S_MISC, (size_t)(cn.Mo + cn.No), &t));
+    term_rows_d = t;
+    term_cols_d = t + cn.Mo;
+    BOF_TRY(copy1d(ctx, term_rows_d, canon_rows_are_m ? term_m : term_n, (size_t)cn.Mo * 4, H2D, ctx->h2d));
+    BOF_TRY(copy1d(ctx, term_cols_d, canon_rows_are_m ? term_n : term_m, (size_t)cn.No * 4, H2D, ctx->h2d));
+    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 3), ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 3), 0));
+  }
+
   // events: 4+g P block uploaded, 8+g P block split, 12+g block computed, 16+g block downloaded, 20+j Q panel
   constexpr int EV_UP = 4, EV_SPLIT = 8, EV_DONE = 12, EV_DOWN = 16, EV_QPAN = 20;
   bool used[NB] = {};
@@ -1107,6 +1124,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   };
   auto finish_block = [&](int i) -> int {
     const int g = i % NB;
+    if (with_terms)  // term_m is added first (kmeans_task.h:74-80): it is the row term iff the canonical rows are m
+      BOF_TRY(launch_add_outer_terms(ctx, ctx->compute, cblk_of(g), rows_of(i), cn.No, cn.No, term_rows_d + (int64_t)i * rb,
+                                     term_cols_d, canon_rows_are_m ? 1 : 0));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
     used[g] = true;
     return BOF_OK;
@@ -1193,6 +1213,13 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
 int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
                   float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc) {
   return host_gemm_impl(ctx, ord, ta, tb, m, n, k, alpha, beta, a, b, c, lda, ldb, ldc, false);
+}
+
+int bof_host_kmeans_dist(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
+                         float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc,
+                         const float* c_l2sq, const float* p_l2sq) {
+  if (ctx && (c_l2sq == nullptr || p_l2sq == nullptr)) return fail(ctx, BOF_EINVAL, "kmeans: c_l2sq / p_l2sq is null");
+  return host_gemm_impl(ctx, ord, ta, tb, m, n, k, alpha, beta, a, b, c, lda, ldb, ldc, false, c_l2sq, p_l2sq);
 }
 
 int bof_host_gemm_devb(bof_ctx* ctx, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha, float beta,

@@ -134,6 +134,8 @@ int launch_idx_widen(bof_ctx* ctx, cudaStream_t s, const int32_t* in, int64_t* o
 // out[c * ldo + r] = in[r * ldi + c] for an rows x cols row-major input
 int launch_transpose(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, const float* in,
                      int64_t ldi, float* out, int64_t ldo);
+int launch_add_outer_terms(bof_ctx* ctx, cudaStream_t s, float* C, int64_t rows, int64_t cols, int64_t ldc,
+                           const float* rowv, const float* colv, int row_first);
 // out = alpha * in^T + beta * out, same indexing as launch_transpose (beta==0: out not read)
 int launch_transpose_axpby(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t cols, float alpha,
                            const float* in, int64_t ldi, float beta, float* out, int64_t ldo);

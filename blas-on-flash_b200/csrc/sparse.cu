@@ -493,6 +493,32 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
 #undef BOF_SPMM
 }
 
+// KMeansTask::execute's two rank-1 updates (include/tasks/kmeans_task.h:74-80) on a row-major block:
+// C[r, c] = (C[r, c] + first) + second with first/second = rowv[r], colv[c] in the order `row_first` says.
+namespace {
+__global__ void __launch_bounds__(256)
+add_outer_terms_kernel(float* __restrict__ C, int64_t rows, int64_t cols, int64_t ldc, const float* __restrict__ rowv,
+                       const float* __restrict__ colv, int row_first) {
+  const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols, c = i - r * cols;
+    float v = C[r * ldc + c];
+    const float a = rowv[r], b = __ldg(colv + c);
+    v = row_first ? __fadd_rn(__fadd_rn(v, a), b) : __fadd_rn(__fadd_rn(v, b), a);
+    C[r * ldc + c] = v;
+  }
+}
+}  // namespace
+
+int launch_add_outer_terms(bof_ctx* ctx, cudaStream_t s, float* C, int64_t rows, int64_t cols, int64_t ldc,
+                           const float* rowv, const float* colv, int row_first) {
+  if (rows == 0 || cols == 0) return BOF_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(rows * cols, 256), (int64_t)ctx->num_sms * 16);
+  add_outer_terms_kernel<<<grid, 256, 0, s>>>(C, rows, cols, ldc, rowv, colv, row_first);
+  BOF_LAUNCH_CHECK(ctx, "add_outer_terms_kernel");
+  return BOF_OK;
+}
+
 int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
                 const int32_t* idx, const int64_t* offs, const float* x, float* y) {
   // 'T' zeroes y first (src/blas/csrgemv.cpp:64); 't' accumulates into y as it is, which is

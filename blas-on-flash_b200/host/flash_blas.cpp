@@ -83,20 +83,14 @@ FBLAS_INT gemm(CHAR mat_ord, CHAR trans_a, CHAR trans_b, FBLAS_UINT m, FBLAS_UIN
 FBLAS_INT kmeans(CHAR mat_ord, CHAR trans_a, CHAR trans_b, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha,
                  FPTYPE beta, flash_ptr<FPTYPE> a, flash_ptr<FPTYPE> b, flash_ptr<FPTYPE> c, FBLAS_UINT lda_a,
                  FBLAS_UINT lda_b, FBLAS_UINT lda_c, FPTYPE* c_l2sq, FPTYPE* p_l2sq, FPTYPE* /*ones*/) {
-  // KMeansTask::execute (reference include/tasks/kmeans_task.h:68-80): the product, then the two
-  // rank-1 updates C(i, j) += c_l2sq[i] and C(i, j) += p_l2sq[j], in that order.
-  const FBLAS_INT rc = gemm(mat_ord, trans_a, trans_b, m, n, k, alpha, beta, a, b, c, lda_a, lda_b, lda_c);
-  if (rc != 0) return rc;
-  const bool col = mat_ord == 'C';
-  const FBLAS_UINT ld = lda_c ? lda_c : (col ? m : n);
-  FPTYPE* C = c.ptr;
-  for (FBLAS_UINT i = 0; i < m; ++i)
-    for (FBLAS_UINT j = 0; j < n; ++j) {
-      FPTYPE& d = col ? C[j * ld + i] : C[i * ld + j];
-      d = d + c_l2sq[i];
-      d = d + p_l2sq[j];
-    }
-  return 0;
+  // KMeansTask::execute (reference include/tasks/kmeans_task.h:68-80): the product, then the two rank-1 updates
+  // C(i, j) += c_l2sq[i] and C(i, j) += p_l2sq[j], in that order -- applied on the device before each block
+  // of C is downloaded.
+  bof_ctx* ctx = flash_context();
+  if (!ctx) return -1;
+  return done("kmeans", bof_host_kmeans_dist(ctx, mat_ord, trans_a, trans_b, (int64_t)m, (int64_t)n, (int64_t)k, alpha,
+                                            beta, a.ptr, b.ptr, c.ptr, (int64_t)lda_a, (int64_t)lda_b, (int64_t)lda_c,
+                                            c_l2sq, p_l2sq));
 }
 
 FBLAS_INT csrmm(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE alpha, FPTYPE beta,

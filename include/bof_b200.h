@@ -207,6 +207,15 @@ int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alp
                         const float* a, const int64_t* ia, const int64_t* ja, const float* b_dev,
                         float* c);
 
+/* flash::kmeans, the distance tile of k-means (include/flash_blas.h:20-25; KMeansTask::execute,
+ * include/tasks/kmeans_task.h:53-82): the product of bof_host_gemm, then C(i, j) += c_l2sq[i] and
+ * C(i, j) += p_l2sq[j] in that order (i over m, j over n), applied to each output block on the device
+ * before it is downloaded.  c_l2sq (m entries) and p_l2sq (n entries) are host arrays. */
+int bof_host_kmeans_dist(bof_ctx* ctx, char mat_ord, char trans_a, char trans_b, int64_t m, int64_t n,
+                         int64_t k, float alpha, float beta, const float* a, const float* b, float* c,
+                         int64_t lda_a, int64_t lda_b, int64_t lda_c, const float* c_l2sq,
+                         const float* p_l2sq);
+
 /* flash::csrgemv (include/flash_blas.h:55-57; src/blas/csrgemv.cpp:82-97). */
 int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a,
                      const int64_t* ia, const int64_t* ja, const float* b, float* c);

@@ -27,7 +27,8 @@ FBLAS_INT gemm(CHAR mat_ord, CHAR trans_a, CHAR trans_b,
 // Distance tile of k-means: C = alpha * op(A) * op(B) + beta * C + c_l2sq 1^T + 1 p_l2sq^T
 //                                                                        [reference flash_blas.h:20-25]
 //   the reference calls it as ('C','T','N', ncenters, npoints, dim, -2, 0, centers, points, dist, ...)
-//   (drivers/kmeans.cpp:36-38); `ones` is accepted for source compatibility and not read.
+//   (drivers/kmeans.cpp:36-38); `ones` is accepted for source compatibility and not read.  The two rank-1
+//   terms are added on the device (bof_host_kmeans_dist) before each block of C is downloaded.
 //   Prefer kmeans_lloyd() below: it never materialises the distance matrix.
 FBLAS_INT kmeans(CHAR mat_ord, CHAR trans_a, CHAR trans_b,
                  FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k,

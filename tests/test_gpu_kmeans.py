@@ -120,3 +120,34 @@ def test_lloyd_iterations_teacher_forced(bof, ctx):
         if ok.all():
             assert oracle.rel_fro(got_c, ref_c) <= TOL
         cent = ref_c
+
+
+@pytest.mark.parametrize("ord_", ["C", "R"])
+def test_distance_tile_flash_kmeans(ctx, ord_):
+    """flash::kmeans / KMeansTask::execute (include/tasks/kmeans_task.h:68-80): D = -2 mu^T X, then += c_l2sq[i],
+    then += p_l2sq[j].  'C' is the reference's own call form ('C','T','N', ncenters, npoints, dim, -2, 0, centers,
+    points, dist; drivers/kmeans.cpp:36-38); the rank-1 terms are added on the device, fp32, in that order."""
+    rng = np.random.default_rng(31)
+    K, P, d = 70, 5000, 48
+    cent = rng.normal(size=(K, d)).astype(np.float32)
+    pts = rng.normal(size=(P, d)).astype(np.float32)
+    c2 = oracle.row_sqnorm(cent); p2 = oracle.row_sqnorm(pts)
+    if ord_ == "C":
+        # column-major: op(A) = centers^T^T ... A is d x K col-major = centers row-major; C is K x P col-major
+        D = np.full(K * P, np.nan, np.float32)
+        ctx.host_kmeans_dist("C", "T", "N", K, P, d, -2.0, 0.0, cent, pts, D, c2, p2, lda=d, ldb=d, ldc=K)
+        got = D.reshape(P, K).T                      # D(i, j) at j*K + i
+        prod = oracle.gemm("C", "T", "N", K, P, d, -2.0, 0.0, cent, pts, np.zeros(K * P, np.float32), d, d, K,
+                           acc64=True).reshape(P, K).T
+    else:
+        D = np.full((K, P), np.nan, np.float32)
+        ctx.host_kmeans_dist("R", "N", "T", K, P, d, -2.0, 0.0, cent, pts, D, c2, p2)
+        got = D
+        prod = oracle.gemm("R", "N", "T", K, P, d, -2.0, 0.0, cent, pts, np.zeros((K, P), np.float32), acc64=True)
+    ref = (prod + c2[:, None]) + p2[None, :]
+    assert oracle.rel_fro(got, ref) <= 1e-5
+    # the argmin over centers of the tile reproduces the oracle's assignment (isamin semantics on ties-free data)
+    a_ref, margin = oracle.kmeans_assign(pts, cent, c2, p2)
+    clear = margin > 1e-3                       # top-2 gap well above fp32 rounding of the distances
+    assert clear.mean() > 0.9
+    assert np.array_equal(np.abs(got).argmin(axis=0)[clear], a_ref[clear])
