@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--size", type=int, default=M_FULL, help="override m=n=k (debug only; invalid as a bench value)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on all CPUs (A/B of the NUMA binding)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,6 +295,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # CPU baseline first: its OpenMP workers are created while the process may still run on every host core
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu, _ = cpu_gemm_sample()
+        except Exception as ex:
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"}
+    from bof_b200 import dist as bdist
+    cpus_before = len(os.sched_getaffinity(0))
+    numa_cpus = 0 if args.no_numa_bind else bdist.bind_to_gpu_numa(local)  # pinned buffers next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -418,12 +429,6 @@ def main():
             extra["csrmm_cfg1"] = csrmm_extra(bof, ctx, torch, pk)
         except Exception as ex:  # the headline must still print
             extra["csrmm_cfg1"] = {"error": repr(ex)}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        try:
-            cpu, _ = cpu_gemm_sample()
-        except Exception as ex:
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"}
 
     if rank == 0:
         line = {
@@ -437,7 +442,8 @@ def main():
                        "l2": "operands (4 GiB each) exceed the 126 MB L2; no flush needed",
                        "spot_check_max_rel_err": spot},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches_dev + launches_e2e), "extra": extra,
+            "gpu_launches": int(launches_dev + launches_e2e),
+            "host": {"cpus": cpus_before, "numa_bound_cpus": numa_cpus}, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -103,3 +103,33 @@ def sum_partials_fixed_order(y_local, group=None):
     for p in parts[1:]:
         out += p.cpu().numpy()
     return out
+
+
+def bind_to_gpu_numa(device_index: int) -> int:
+    """Pin the calling process to the CPUs NVML reports as local to CUDA device `device_index`, so that the pinned
+    host buffers it allocates afterwards sit on the NUMA node next to that GPU's PCIe root (one process per GPU:
+    otherwise every rank's DMA may cross the socket interconnect).  Returns the number of CPUs in the new
+    affinity mask, 0 if NVML or the affinity call is unavailable (nothing changed)."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%08X:%02X:%02X.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0

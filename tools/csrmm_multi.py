@@ -30,6 +30,9 @@ def main():
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    g.load_package()
+    from bof_b200 import dist as _bd
+    _bd.bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     bof = g.load_package()
