@@ -147,7 +147,7 @@ class Drainer {
 
 namespace {
 
-constexpr int kGemmRing = 4;  // P/C block generations in flight in bof_host_gemm
+constexpr int kGemmRing = 5;  // P/C block generations in flight in bof_host_gemm
 
 thread_local std::string g_create_err;
 
@@ -176,7 +176,7 @@ enum Slot {
   S_WS = 18,       // kernel workspaces
   S_OUT0 = 19, S_OUT1, S_OUT2, S_MISC,
   // host gemm: ring of kGemmRing generations (g added to the slot id)
-  S_PRAW = 24, S_PPLANES = 28, S_GCBLK = 32,
+  S_PRAW = 24, S_PPLANES = 30, S_GCBLK = 32,
 };
 
 cudaEvent_t get_event(bof_ctx* ctx, size_t i) {
@@ -186,6 +186,34 @@ cudaEvent_t get_event(bof_ctx* ctx, size_t i) {
     ctx->events.push_back(e);
   }
   return ctx->events[i];
+}
+
+// ---- optional timeline of a host pipeline (BOF_TRACE=1) ----
+bool trace_on() {
+  static const bool on = getenv("BOF_TRACE") != nullptr;
+  return on;
+}
+void trace_mark(bof_ctx* ctx, cudaStream_t s, const char* what, int idx) {
+  if (!trace_on()) return;
+  cudaEvent_t e = nullptr;
+  if (!ctx->trace_pool.empty()) { e = ctx->trace_pool.back(); ctx->trace_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  ctx->trace.push_back({e, what, idx});
+}
+void trace_dump(bof_ctx* ctx, const char* title) {
+  if (!trace_on() || ctx->trace.empty()) return;
+  std::vector<std::pair<float, size_t>> order;
+  for (size_t i = 0; i < ctx->trace.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->trace[0].ev, ctx->trace[i].ev);
+    order.push_back({ms, i});
+  }
+  std::sort(order.begin(), order.end());
+  std::fprintf(stderr, "[bof trace] %s\n", title);
+  for (auto& o : order) std::fprintf(stderr, "[bof trace] %9.3f ms  %s %d\n", o.first, ctx->trace[o.second].what, ctx->trace[o.second].idx);
+  for (auto& m : ctx->trace) ctx->trace_pool.push_back(m.ev);
+  ctx->trace.clear();
 }
 
 bool host_is_pinned(const void* p) {
@@ -595,6 +623,8 @@ int bof_ctx_destroy(bof_ctx* ctx) {
   for (int i = 0; i < bof_ctx::kSlots; ++i)
     if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
   for (auto ev : ctx->events) cudaEventDestroy(ev);
+  for (auto& m : ctx->trace) cudaEventDestroy(m.ev);
+  for (auto ev : ctx->trace_pool) cudaEventDestroy(ev);
   delete ctx->drainer;  // joins its thread before the rings go away
   delete ctx->pool;
   delete ctx->pool_out;
@@ -1073,8 +1103,10 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, 3), 0));
   }
 
-  // events: 4+g P block uploaded, 8+g P block split, 12+g block computed, 16+g block downloaded, 20+j Q panel
-  constexpr int EV_UP = 4, EV_SPLIT = 8, EV_DONE = 12, EV_DOWN = 16, EV_QPAN = 20;
+  // events: 8+g P block uploaded, 16+g P block split, 24+g block computed, 32+g block downloaded, 40+j Q panel
+  // (reused for the column slabs of the last block)
+  constexpr int EV_UP = 8, EV_SPLIT = 16, EV_DONE = 24, EV_DOWN = 32, EV_QPAN = 40;
+  static_assert(kGemmRing <= 8, "event ids are spaced for at most 8 generations");
   bool used[NB] = {};
   int64_t q_sr = 1, q_sk = 1;  // strides of the raw Q copy on the device
 
@@ -1090,6 +1122,7 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     if (beta != 0.f)
       BOF_TRY(copy2d(ctx, cblk_of(g), (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_UP + g), ctx->h2d));
+    trace_mark(ctx, ctx->h2d, "h2d: P block landed", i);
     return BOF_OK;
   };
   // compute of block i against Q rows [n0, n1) (the whole Q when not panelled); `first`/`last` bracket the block
@@ -1115,8 +1148,11 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     if (tensor) {
       GemmEpilogue ep;
       ep.alpha = alpha; ep.beta = beta; ep.C = cblk_of(g) + n0; ep.ldc = cn.No;
-      return launch_gemm_tc(ctx, ctx->compute, cg, rows, n1 - n0, K, kp, p_hi_of(g), p_lo_of(g), q_hi + n0 * kp,
-                            q_lo + n0 * kp, ep, k_chunk_of(ctx));
+      trace_mark(ctx, ctx->compute, "compute: gemm start, first block", i0);
+      const int rc = launch_gemm_tc(ctx, ctx->compute, cg, rows, n1 - n0, K, kp, p_hi_of(g), p_lo_of(g), q_hi + n0 * kp,
+                                    q_lo + n0 * kp, ep, k_chunk_of(ctx));
+      trace_mark(ctx, ctx->compute, "compute: gemm end, rows", (int)rows);
+      return rc;
     }
     const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;  // cnt == 1 on this path
     return launch_gemm_ffma(ctx, ctx->compute, rows, n1 - n0, K, alpha, praw[g], p_sr, p_sk, qraw + n0 * q_sr, q_sk, q_sr,
@@ -1137,6 +1173,7 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_DONE + g), 0));
     BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk_of(g), (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
+    trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
     return BOF_OK;
   };
 
@@ -1145,7 +1182,8 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // remaining panels; block 0 is computed panel by panel as they land, so only one panel and one P block of
   // PCIe time are exposed before the tensor cores start.
   const bool q_panels = tensor && !q_on_device && (size_t)cn.No * K * 4 >= (256u << 20);
-  const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, 8), 256)) : cn.No;
+  static const int64_t n_q_panels = getenv("BOF_GEMM_QPANELS") ? std::min(8, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 8;
+  const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, n_q_panels), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
   // Every panel is kept as its own tight block at qraw + n0*K: [rows x K] when Q is K-major in the source,
   // [K x rows] (a column range of the stored matrix, pitched copy) when it is not.
@@ -1156,6 +1194,7 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     else BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &pan_sr[j], &pan_sk[j], ctx->h2d));
     if (n_qpan == 1) { q_sr = pan_sr[0]; q_sk = pan_sk[0]; }
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->h2d));
+    trace_mark(ctx, ctx->h2d, "h2d: Q panel landed", j);
     return BOF_OK;
   };
   auto split_q_panel = [&](int j) -> int {
@@ -1169,7 +1208,11 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // computed against each panel as it lands (compute order = arrival order), so the tensor cores start after
   // one panel + one block of PCIe time and stay fed while the rest of Q uploads: every new panel unlocks one
   // tile per prologue block.
-  const int npro = n_qpan > 1 ? std::min({nblk, NB, n_qpan}) : 1;  // blocks handled by the prologue
+  trace_mark(ctx, ctx->h2d, "start", 0);
+  // One generation stays out of the prologue: the prologue blocks all finish together (with the last panel), so
+  // the first steady-state block would otherwise wait for a whole C block to be downloaded (11 ms at 32768^3,
+  // seen with BOF_TRACE=1) before it could reuse generation 0.
+  const int npro = n_qpan > 1 ? std::min({nblk, NB - 1, n_qpan}) : 1;  // blocks handled by the prologue
   auto pan = [&](int j, int64_t* n0, int64_t* n1) { *n0 = (int64_t)j * qpan_rows; *n1 = std::min(cn.No, *n0 + qpan_rows); };
   for (int t = 0; t < n_qpan; ++t) {
     BOF_TRY(upload_q_panel(t));
@@ -1196,16 +1239,44 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   }
   // ---- steady state: Q complete; keep NB blocks in flight, fetch the oldest before reusing its buffers ----
   int next_fetch = 0;
+  int fetch_end = nblk;  // blocks [next_fetch, fetch_end) still have to be downloaded whole
   for (int i = npro; i < nblk; ++i) {
     if (next_fetch < i) BOF_TRY(fetch_block(next_fetch++));            // keeps the downloads flowing
     while (next_fetch <= i - NB) BOF_TRY(fetch_block(next_fetch++));   // block i-NB owned these buffers
     BOF_TRY(upload_block(i));
     BOF_TRY(prepare_block(i));
+    if (i == nblk - 1 && tensor && cn.No >= 2048) {
+      // Drain: the last block is multiplied and downloaded in four column slabs, so only the last slab's
+      // download (a quarter of a block) is exposed after the tensor cores stop.
+      const int g = i % NB;
+      const int64_t r0 = (int64_t)i * rb, rows = rows_of(i);
+      const int64_t slab = round_up<int64_t>(ceil_div<int64_t>(cn.No, 4), 256);
+      while (next_fetch < i) BOF_TRY(fetch_block(next_fetch++));  // d2h is FIFO: earlier blocks first
+      int j = 0;
+      for (int64_t n0 = 0; n0 < cn.No; n0 += slab, ++j) {
+        const int64_t n1 = std::min(cn.No, n0 + slab);
+        BOF_TRY(gemm_blocks(i, 1, n0, n1));
+        if (with_terms)
+          BOF_TRY(launch_add_outer_terms(ctx, ctx->compute, cblk_of(g) + n0, rows, n1 - n0, cn.No, term_rows_d + r0,
+                                         term_cols_d + n0, canon_rows_are_m ? 1 : 0));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->compute));
+        BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_QPAN + j), 0));
+        BOF_TRY(copy2d(ctx, c + r0 * cn.ldc + n0, (size_t)cn.ldc * 4, cblk_of(g) + n0, (size_t)cn.No * 4, (size_t)(n1 - n0) * 4,
+                       (size_t)rows, D2H, ctx->d2h));
+        trace_mark(ctx, ctx->d2h, "d2h: last block, slab downloaded", j);
+      }
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
+      used[g] = true;
+      fetch_end = i;
+      break;
+    }
     BOF_TRY(gemm_blocks(i, 1, 0, cn.No));
     BOF_TRY(finish_block(i));
   }
-  while (next_fetch < nblk) BOF_TRY(fetch_block(next_fetch++));
+  while (next_fetch < fetch_end) BOF_TRY(fetch_block(next_fetch++));
   BOF_TRY(sync_all(ctx));
+  trace_dump(ctx, "bof_host_gemm");
   stats_end(ctx);
   return call_guard.done();
 }

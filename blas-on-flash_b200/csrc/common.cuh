@@ -59,6 +59,10 @@ struct bof_ctx {
   void* slot_ptr[kSlots] = {};
   size_t slot_bytes[kSlots] = {};
   std::vector<cudaEvent_t> events;
+  // BOF_TRACE=1: timing events recorded along a host pipeline, printed (ms since the first) when it ends
+  struct TraceMark { cudaEvent_t ev; const char* what; int idx; };
+  std::vector<TraceMark> trace;
+  std::vector<cudaEvent_t> trace_pool;
   // CUDA-event bracket of the most recent tensor-core GEMM kernel (for the roofline figure)
   cudaEvent_t tk0 = nullptr, tk1 = nullptr;
   bool tk_valid = false;
