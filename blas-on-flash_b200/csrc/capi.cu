@@ -838,6 +838,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
   CallGuard call_guard(ctx);
+  trace_mark(ctx, ctx->h2d, "start", 0);
   const int64_t out_rows = trans_a == 'N' ? m : n;   // rows of C
   const int64_t in_rows = trans_a == 'N' ? n : m;    // rows of B
   if (out_rows == 0 || k == 0) { stats_end(ctx); return call_guard.done(); }
@@ -868,6 +869,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
   }
 
+  trace_mark(ctx, ctx->h2d, "h2d: dense operand landed", 0);
   const int64_t* offs_host = ia;
   const int64_t nnz = ia[m] - ia[0];
   std::vector<int64_t> tr_offs_host;  // only for 'T'
@@ -959,7 +961,9 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
     if (used[g]) {
       BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_done, 0));   // inputs of block i-2 consumed
-      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_down, 0));   // its C rows left the device
+      // Only an upload of old C rows (beta != 0) touches the C buffer from this stream; waiting for the download
+      // unconditionally idled the H2D engine ~9 ms every other block (BOF_TRACE timeline, cfg-3: 419 -> 37x ms).
+      if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_down, 0));   // its C rows left the device
     }
     BOF_TRY(copy1d(ctx, offs_d[g], offs_host + r0, (size_t)(rows + 1) * 8, H2D, ctx->h2d));
     BOF_TRY(copy1d(ctx, idx64_d[g], ja + z0, (size_t)bnnz * 8, H2D, ctx->h2d));
@@ -970,8 +974,10 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
       else BOF_TRY(copy1d(ctx, c_io, c + r0 * k, (size_t)rows * k * 4, H2D, ctx->h2d));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
+    trace_mark(ctx, ctx->h2d, "h2d: A block landed", i);
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_up, 0));
     if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_down, 0));
+    trace_mark(ctx, ctx->compute, "compute: block start", i);
     BOF_TRY(launch_idx_narrow(ctx, ctx->compute, idx64_d[g], idx32_d[g], bnnz));
     if (colmaj) {
       BOF_TRY(launch_spmm_rm(ctx, ctx->compute, rows, k, 1.f, vals_d[g], idx32_d[g], offs_d[g], Bd, k, 0.f, cblk[g], k));
@@ -980,6 +986,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
       BOF_TRY(launch_spmm_rm(ctx, ctx->compute, rows, k, alpha, vals_d[g], idx32_d[g], offs_d[g], Bd, k, beta, cblk[g], k));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
+    trace_mark(ctx, ctx->compute, "compute: block end", i);
     used[g] = true;
     return BOF_OK;
   };
@@ -991,6 +998,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     if (colmaj) BOF_TRY(copy2d(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, D2H, ctx->d2h));
     else BOF_TRY(copy1d(ctx, c + r0 * k, c_io, (size_t)rows * k * 4, D2H, ctx->d2h));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->d2h));
+    trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
     return BOF_OK;
   };
   if (nblk > 0) BOF_TRY(stage_block(0));
@@ -999,6 +1007,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     BOF_TRY(fetch_block(i));
   }
   BOF_TRY(sync_all(ctx));
+  trace_dump(ctx, "bof_host_csrmm");
   stats_end(ctx);
   return call_guard.done();
 }
