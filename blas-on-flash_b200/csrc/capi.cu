@@ -76,10 +76,24 @@ class CopyPool {
 };
 
 void drain_copy_out(bof_ctx* ctx, StageSlot* sl);  // defined below (needs host_rows_copy)
+void trace_host(bof_ctx* ctx, const char* what, long idx);  // BOF_TRACE wall-clock mark (any thread)
 
-// One background thread per context: waits for a device->host chunk to land in its pinned slot, copies it
-// to the caller's (pageable) buffer and returns the slot to the ring, so that the calling thread can keep
-// staging uploads meanwhile.  The writer side of the reference's IoExecutor threads.
+// One background thread per context runs the device->host side of the pageable path -- the writer half of the
+// reference's IoExecutor threads.  The calling thread only describes a transfer (D2HJob) and goes on staging
+// uploads; this thread enqueues the chunked copies into the pinned ring on the job's stream (after `wait_ev`),
+// records `record_ev` behind them, and copies every chunk out to the caller's buffer once its DMA has landed
+// (the copy-out of chunk c overlaps the DMA of the chunks after it).  A consumer of `record_ev` first calls
+// wait_issued(ticket): CUDA ignores waits on events that have not been recorded yet.
+struct D2HJob {
+  char* host = nullptr; size_t hpitch = 0;
+  const char* dev = nullptr; size_t dpitch = 0;
+  size_t width = 0, rows = 0;
+  bool flat = false;
+  cudaStream_t s = nullptr;
+  cudaEvent_t wait_ev = nullptr, record_ev = nullptr;
+  uint64_t id = 0;
+};
+
 class Drainer {
  public:
   explicit Drainer(bof_ctx* ctx) : ctx_(ctx), th_([this] { loop(); }) {}
@@ -91,56 +105,107 @@ class Drainer {
     cv_.notify_all();
     th_.join();
   }
-  void wait_free(StageSlot& sl) {
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_free_.wait(lk, [&] { return !sl.in_flight; });
-  }
-  void push(StageSlot* sl) {
+  uint64_t push(D2HJob job) {
+    uint64_t id;
     {
       std::lock_guard<std::mutex> lk(mu_);
-      sl->in_flight = true;
-      q_.push_back(sl);
+      id = job.id = ++pushed_;
+      q_.push_back(job);
     }
     cv_.notify_one();
+    return id;
   }
+  void wait_issued(uint64_t id) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return issued_ >= id; });
+  }
+  void wait_all_issued() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return issued_ >= pushed_; });
+  }
+  // every pushed transfer has reached the caller's memory; returns false if one of them failed since the last call
   bool wait_idle() {
     std::unique_lock<std::mutex> lk(mu_);
-    cv_free_.wait(lk, [&] { return q_.empty() && !busy_; });
+    cv_done_.wait(lk, [&] { return q_.empty() && !busy_; });
     const bool ok = ok_;
     ok_ = true;
     return ok;
   }
 
  private:
+  void drain(StageSlot& sl) {
+    if (!sl.in_flight) return;
+    if (cudaEventSynchronize(sl.ev) == cudaSuccess) drain_copy_out(ctx_, &sl);
+    else { cudaGetLastError(); failed_ = true; }
+    sl.in_flight = false;
+    sl.out_dst = nullptr;
+  }
+  void run(const D2HJob& j) {
+    std::vector<StageSlot>& ring = ctx_->stage_out;  // touched by this thread only
+    const size_t cap = ctx_->cfg.stage_bytes, total = j.width * j.rows;
+    // a flat transfer is cut into cap-sized pseudo rows
+    const size_t w = j.flat ? std::min(cap, total) : j.width;
+    const size_t total_rows = j.flat ? (total + w - 1) / w : j.rows;
+    const size_t rows_per_chunk = std::max<size_t>(1, cap / w);
+    bool ok = true;
+    trace_host(ctx_, "drainer: job start", (long)j.id);
+    if (j.wait_ev) ok = cudaStreamWaitEvent(j.s, j.wait_ev, 0) == cudaSuccess && ok;
+    for (size_t r0 = 0; r0 < total_rows; r0 += rows_per_chunk) {
+      const size_t rows = std::min(rows_per_chunk, total_rows - r0);
+      StageSlot& sl = ring[next_slot_++ % ring.size()];
+      drain(sl);
+      if (j.flat) {
+        const size_t bytes = std::min(total - r0 * w, rows * w);  // the last pseudo row may be short
+        ok = cudaMemcpyAsync(sl.ptr, j.dev + r0 * w, bytes, cudaMemcpyDeviceToHost, j.s) == cudaSuccess && ok;
+        sl.out_dst = j.host + r0 * w; sl.out_pitch = bytes; sl.out_width = bytes; sl.out_rows = 1;
+      } else {
+        ok = cudaMemcpy2DAsync(sl.ptr, w, j.dev + r0 * j.dpitch, j.dpitch, w, rows, cudaMemcpyDeviceToHost, j.s) == cudaSuccess && ok;
+        sl.out_dst = j.host + r0 * j.hpitch; sl.out_pitch = j.hpitch; sl.out_width = w; sl.out_rows = rows;
+      }
+      ok = cudaEventRecord(sl.ev, j.s) == cudaSuccess && ok;
+      sl.in_flight = true;
+    }
+    if (j.record_ev) ok = cudaEventRecord(j.record_ev, j.s) == cudaSuccess && ok;
+    trace_host(ctx_, "drainer: job issued", (long)j.id);
+    if (!ok) { cudaGetLastError(); failed_ = true; }
+  }
   void loop() {
     cudaSetDevice(ctx_->device);
     for (;;) {
-      StageSlot* sl = nullptr;
+      D2HJob job;
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
         if (q_.empty()) return;  // stop requested and nothing left
-        sl = q_.front();
+        job = q_.front();
         q_.pop_front();
         busy_ = true;
       }
-      const bool landed = cudaEventSynchronize(sl->ev) == cudaSuccess;
-      if (landed) drain_copy_out(ctx_, sl);
+      run(job);
+      bool more;
       {
         std::lock_guard<std::mutex> lk(mu_);
-        if (!landed) ok_ = false;
-        sl->in_flight = false;
-        sl->out_dst = nullptr;
+        issued_ = job.id;
+        more = !q_.empty();
+      }
+      cv_done_.notify_all();
+      if (!more)  // nothing queued behind it: finish the chunks still in flight (a later job would recycle them)
+        for (auto& sl : ctx_->stage_out) drain(sl);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (failed_) { ok_ = false; failed_ = false; }
         busy_ = false;
       }
-      cv_free_.notify_all();
+      cv_done_.notify_all();
     }
   }
   bof_ctx* ctx_;
   std::mutex mu_;
-  std::condition_variable cv_, cv_free_;
-  std::deque<StageSlot*> q_;
-  bool stop_ = false, busy_ = false, ok_ = true;
+  std::condition_variable cv_, cv_done_;
+  std::deque<D2HJob> q_;
+  uint64_t pushed_ = 0, issued_ = 0;
+  size_t next_slot_ = 0;
+  bool stop_ = false, busy_ = false, ok_ = true, failed_ = false;
   std::thread th_;
 };
 }  // namespace bof
@@ -195,13 +260,28 @@ bool trace_on() {
 }
 void trace_mark(bof_ctx* ctx, cudaStream_t s, const char* what, int idx) {
   if (!trace_on()) return;
+  if (ctx->trace.empty()) ctx->trace_t0 = now_ms();
   cudaEvent_t e = nullptr;
   if (!ctx->trace_pool.empty()) { e = ctx->trace_pool.back(); ctx->trace_pool.pop_back(); }
   else if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, s);
   ctx->trace.push_back({e, what, idx});
 }
+}  // namespace
+namespace bof {
+void trace_host(bof_ctx* ctx, const char* what, long idx) {
+  if (!trace_on()) return;
+  std::lock_guard<std::mutex> lk(ctx->host_trace_mu);
+  ctx->host_trace.push_back({now_ms() - ctx->trace_t0, what, idx});
+}
+}  // namespace bof
+namespace {
 void trace_dump(bof_ctx* ctx, const char* title) {
+  if (trace_on()) {
+    std::lock_guard<std::mutex> lk(ctx->host_trace_mu);
+    for (auto& h : ctx->host_trace) std::fprintf(stderr, "[bof host ] %9.3f ms  %s %ld\n", h.ms, h.what, h.idx);
+    ctx->host_trace.clear();
+  }
   if (!trace_on() || ctx->trace.empty()) return;
   std::vector<std::pair<float, size_t>> order;
   for (size_t i = 0; i < ctx->trace.size(); ++i) {
@@ -225,6 +305,13 @@ bool host_is_pinned(const void* p) {
   return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
 }
 
+int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring);
+// Both rings are created at the first staged transfer of a context: cudaMallocHost in the middle of a pipeline waits
+// for the device (147 ms behind the prologue kernels at 32768^3, BOF_TRACE).
+int ensure_rings(bof_ctx* ctx) {
+  BOF_TRY(ensure_ring(ctx, ctx->stage_in));
+  return ensure_ring(ctx, ctx->stage_out);
+}
 int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
   if (!ring.empty()) return BOF_OK;
   ring.resize((size_t)ctx->cfg.n_stage_bufs);
@@ -326,64 +413,94 @@ int drain_slot(bof_ctx* ctx, StageSlot& sl) {
   return BOF_OK;
 }
 
-// Pageable host memory (e.g. the mmap behind a flash_ptr) <-> device through the pinned ring: the host
-// memcpy of chunk i+1 overlaps the DMA of chunk i.  Blocks the calling thread, like the reference's
-// synchronous FlashFileHandle::read into a cache buffer, but keeps the copy engines at work.
-int staged_copy(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
-                cudaMemcpyKind kind, cudaStream_t s) {
-  const bool h2d = kind == cudaMemcpyHostToDevice;
-  std::vector<StageSlot>& ring = h2d ? ctx->stage_in : ctx->stage_out;
-  BOF_TRY(ensure_ring(ctx, ring));
+// Pageable host memory (e.g. the mmap behind a flash_ptr) -> device through the pinned ring: the host memcpy of
+// chunk i+1 overlaps the DMA of chunk i.  Blocks the calling thread, like the reference's synchronous
+// FlashFileHandle::read into a cache buffer, but keeps the copy engine at work.
+int staged_upload(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                  cudaStream_t s) {
+  std::vector<StageSlot>& ring = ctx->stage_in;
+  BOF_TRY(ensure_rings(ctx));
   const size_t cap = ctx->cfg.stage_bytes;
   // view the transfer as rows of `w` bytes; a flat transfer is cut into cap-sized pseudo rows
   const bool flat = (dpitch == width && spitch == width) || height == 1;
   const size_t w = flat ? std::min(cap, width * height) : width;
   const size_t total_rows = flat ? ceil_div<size_t>(width * height, w) : height;
-  const size_t hp = flat ? w : (h2d ? spitch : dpitch), dp = flat ? w : (h2d ? dpitch : spitch);
   const size_t rows_per_chunk = std::max<size_t>(1, cap / w);
   const size_t flat_bytes = width * height;
-  char* host = const_cast<char*>(static_cast<const char*>(h2d ? src : dst));
-  char* dev = const_cast<char*>(static_cast<const char*>(h2d ? dst : src));
+  char* host = const_cast<char*>(static_cast<const char*>(src));
+  char* dev = static_cast<char*>(dst);
   size_t slot_i = 0;
   for (size_t r0 = 0; r0 < total_rows; r0 += rows_per_chunk, ++slot_i) {
     const size_t rows = std::min(rows_per_chunk, total_rows - r0);
     StageSlot& sl = ring[slot_i % ring.size()];
-    if (h2d) BOF_TRY(drain_slot(ctx, sl));
-    else ctx->drainer->wait_free(sl);  // the drainer thread hands the slot back after copying it out
-    // the last pseudo row of a flat transfer may be short
-    const size_t bytes = flat ? std::min(flat_bytes - r0 * w, rows * w) : rows * w;
-    if (h2d) {
-      if (flat) host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * w, bytes, bytes, 1, true);
-      else host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * hp, hp, w, rows, true);
-      if (flat) BOF_CUDA(ctx, cudaMemcpyAsync(dev + r0 * w, sl.ptr, bytes, kind, s));
-      else BOF_CUDA(ctx, cudaMemcpy2DAsync(dev + r0 * dp, dp, sl.ptr, w, w, rows, kind, s));
+    BOF_TRY(drain_slot(ctx, sl));
+    if (flat) {
+      const size_t bytes = std::min(flat_bytes - r0 * w, rows * w);  // the last pseudo row may be short
+      host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * w, bytes, bytes, 1, true);
+      BOF_CUDA(ctx, cudaMemcpyAsync(dev + r0 * w, sl.ptr, bytes, cudaMemcpyHostToDevice, s));
     } else {
-      if (flat) {
-        BOF_CUDA(ctx, cudaMemcpyAsync(sl.ptr, dev + r0 * w, bytes, kind, s));
-        sl.out_dst = host + r0 * w; sl.out_pitch = bytes; sl.out_width = bytes; sl.out_rows = 1;
-      } else {
-        BOF_CUDA(ctx, cudaMemcpy2DAsync(sl.ptr, w, dev + r0 * dp, dp, w, rows, kind, s));
-        sl.out_dst = host + r0 * hp; sl.out_pitch = hp; sl.out_width = w; sl.out_rows = rows;
-      }
+      host_rows_copy(ctx, static_cast<char*>(sl.ptr), host + r0 * spitch, spitch, w, rows, true);
+      BOF_CUDA(ctx, cudaMemcpy2DAsync(dev + r0 * dpitch, dpitch, sl.ptr, w, w, rows, cudaMemcpyHostToDevice, s));
     }
     BOF_CUDA(ctx, cudaEventRecord(sl.ev, s));
-    if (h2d) sl.in_flight = true;
-    else ctx->drainer->push(&sl);  // copied out in the background; sync_all()/drain_wait() joins
+    sl.in_flight = true;
   }
   return BOF_OK;
 }
 
+bool wants_staging(const bof_ctx* ctx, const void* host, size_t dpitch, size_t spitch, size_t width, size_t height) {
+  const bool flat = (dpitch == width && spitch == width) || height == 1;
+  return width * height >= (256u << 10) && (flat || width <= ctx->cfg.stage_bytes) && !host_is_pinned(host);
+}
+
+// Device -> host transfer on stream `s`, ordered after `wait_ev` (may be null); `record_ev` (may be null) is
+// recorded on `s` behind it.  A pinned destination is enqueued right here.  A pageable one is handed to the
+// drainer thread, which enqueues it chunk by chunk through the pinned ring while the calling thread goes on;
+// *ticket then identifies the transfer and d2h_fence(ticket) must precede any use of `record_ev` (and any
+// re-recording of `wait_ev`).  sync_all() completes every transfer.
+int d2h_transfer(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                 cudaStream_t s, cudaEvent_t wait_ev, cudaEvent_t record_ev, uint64_t* ticket) {
+  if (ticket) *ticket = 0;
+  const bool empty = width == 0 || height == 0;
+  ctx->stats.d2h_bytes += (double)width * height;
+  if (empty || !wants_staging(ctx, dst, dpitch, spitch, width, height)) {
+    if (wait_ev) BOF_CUDA(ctx, cudaStreamWaitEvent(s, wait_ev, 0));
+    if (!empty) {
+      if (dpitch == width && spitch == width) BOF_CUDA(ctx, cudaMemcpyAsync(dst, src, width * height, cudaMemcpyDeviceToHost, s));
+      else BOF_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, s));
+    }
+    if (record_ev) BOF_CUDA(ctx, cudaEventRecord(record_ev, s));
+    return BOF_OK;
+  }
+  BOF_TRY(ensure_rings(ctx));
+  D2HJob j;
+  j.host = static_cast<char*>(dst); j.hpitch = dpitch;
+  j.dev = static_cast<const char*>(src); j.dpitch = spitch;
+  j.width = width; j.rows = height;
+  j.flat = (dpitch == width && spitch == width) || height == 1;
+  j.s = s; j.wait_ev = wait_ev; j.record_ev = record_ev;
+  const uint64_t id = ctx->drainer->push(j);
+  if (ticket) *ticket = id;
+  return BOF_OK;
+}
+
+void d2h_fence(bof_ctx* ctx, uint64_t ticket) {
+  if (ticket == 0 || !ctx->drainer) return;
+  trace_host(ctx, "caller: fence enter", (long)ticket);
+  ctx->drainer->wait_issued(ticket);
+  trace_host(ctx, "caller: fence leave", (long)ticket);
+}
+
 // pitched host<->device copy; collapses to a flat copy when both sides are tight.  Pinned host memory
-// is copied asynchronously in place; pageable memory goes through the staging ring.
+// is copied asynchronously in place; pageable memory goes through the staging rings.
 int copy2d(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
            size_t height, cudaMemcpyKind kind, cudaStream_t s) {
   if (width == 0 || height == 0) return BOF_OK;
-  if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (double)width * height;
-  else if (kind == cudaMemcpyDeviceToHost) ctx->stats.d2h_bytes += (double)width * height;
-  const void* host = kind == cudaMemcpyHostToDevice ? src : dst;
-  const bool flat = (dpitch == width && spitch == width) || height == 1;
-  const bool staged = width * height >= (256u << 10) && (flat || width <= ctx->cfg.stage_bytes) && !host_is_pinned(host);
-  if (staged) return staged_copy(ctx, dst, dpitch, src, spitch, width, height, kind, s);
+  if (kind == cudaMemcpyDeviceToHost) return d2h_transfer(ctx, dst, dpitch, src, spitch, width, height, s, nullptr, nullptr, nullptr);
+  if (kind == cudaMemcpyHostToDevice) {
+    ctx->stats.h2d_bytes += (double)width * height;
+    if (wants_staging(ctx, src, dpitch, spitch, width, height)) return staged_upload(ctx, dst, dpitch, src, spitch, width, height, s);
+  }
   if (dpitch == width && spitch == width) {
     BOF_CUDA(ctx, cudaMemcpyAsync(dst, src, width * height, kind, s));
   } else {
@@ -412,6 +529,7 @@ int drain_wait(bof_ctx* ctx) {
 }
 
 int sync_all(bof_ctx* ctx) {
+  if (ctx->drainer) ctx->drainer->wait_all_issued();  // the drainer may still be enqueueing copies on the streams
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
@@ -421,12 +539,12 @@ int sync_all(bof_ctx* ctx) {
 // After a failed call nothing of it may still be running: queued copies and the drainer thread reference the
 // caller's host buffers and the context's slots.  Keeps the recorded error message.
 void quiesce(bof_ctx* ctx) {
+  if (ctx->drainer) ctx->drainer->wait_all_issued();
   cudaStreamSynchronize(ctx->h2d);
   cudaStreamSynchronize(ctx->compute);
   cudaStreamSynchronize(ctx->d2h);
   if (ctx->drainer) ctx->drainer->wait_idle();
-  for (auto* ring : {&ctx->stage_in, &ctx->stage_out})
-    for (auto& sl : *ring) sl.in_flight = false;
+  for (auto& sl : ctx->stage_in) sl.in_flight = false;
   cudaGetLastError();
 }
 
@@ -954,12 +1072,14 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   // uploaded and launched before block i is downloaded, so a (host-blocking) staged download of
   // block i overlaps the kernel of block i+1 and the copy engines never wait on the host.
   bool used[2] = {false, false};
+  uint64_t down_ticket[2] = {0, 0};  // pageable C: the drainer enqueues the download and records ev_down
   auto stage_block = [&](int i) -> int {
     const int g = i & 1;
     const int64_t r0 = cuts[i], r1 = cuts[i + 1], rows = r1 - r0;
     const int64_t z0 = offs_host[r0] - offs_host[0], z1 = offs_host[r1] - offs_host[0], bnnz = z1 - z0;
     cudaEvent_t ev_up = get_event(ctx, 4 + g), ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
     if (used[g]) {
+      d2h_fence(ctx, down_ticket[g]);  // ev_down of block i-2 has been recorded (and ev_done may be re-recorded)
       BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ev_done, 0));   // inputs of block i-2 consumed
       // Only an upload of old C rows (beta != 0) touches the C buffer from this stream; waiting for the download
       // unconditionally idled the H2D engine ~9 ms every other block (BOF_TRACE timeline, cfg-3: 419 -> 37x ms).
@@ -994,10 +1114,9 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     const int g = i & 1;
     const int64_t r0 = cuts[i], rows = cuts[i + 1] - r0;
     float* c_io = colmaj ? cblk_t[g] : cblk[g];
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, 6 + g), 0));
-    if (colmaj) BOF_TRY(copy2d(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, D2H, ctx->d2h));
-    else BOF_TRY(copy1d(ctx, c + r0 * k, c_io, (size_t)rows * k * 4, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->d2h));
+    cudaEvent_t ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
+    if (colmaj) BOF_TRY(d2h_transfer(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
+    else BOF_TRY(d2h_transfer(ctx, c + r0 * k, (size_t)rows * k * 4, c_io, (size_t)rows * k * 4, (size_t)rows * k * 4, 1, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
     trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
     return BOF_OK;
   };
@@ -1117,17 +1236,21 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   constexpr int EV_UP = 8, EV_SPLIT = 16, EV_DONE = 24, EV_DOWN = 32, EV_QPAN = 40;
   static_assert(kGemmRing <= 8, "event ids are spaced for at most 8 generations");
   bool used[NB] = {};
+  uint64_t down_ticket[NB] = {};  // pageable C: the drainer enqueues the download and records EV_DOWN
   int64_t q_sr = 1, q_sk = 1;  // strides of the raw Q copy on the device
 
   auto upload_block = [&](int i) -> int {  // P rows (+ old C rows when beta != 0) of block i
     const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, r1 = std::min(cn.Mo, r0 + rb), rows = r1 - r0;
     if (used[g]) {
+      d2h_fence(ctx, down_ticket[g]);  // EV_DOWN of block i-NB has been recorded; its EV_DONE may be re-recorded
       BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, (tensor ? EV_SPLIT : EV_DONE) + g), 0));  // raw P of block i-NB consumed
       if (beta != 0.f) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, EV_DOWN + g), 0));       // C buffer free
     }
     int64_t p_sr, p_sk;
+    trace_host(ctx, "caller: upload P block begin", i);
     BOF_TRY(upload_rows(cn.psrc, cn.p_sr, cn.p_sk, r0, r1, praw[g], &p_sr, &p_sk, ctx->h2d));
+    trace_host(ctx, "caller: upload P block end", i);
     if (beta != 0.f)
       BOF_TRY(copy2d(ctx, cblk_of(g), (size_t)cn.No * 4, c + r0 * cn.ldc, (size_t)cn.ldc * 4, (size_t)cn.No * 4, (size_t)rows, H2D, ctx->h2d));
     BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_UP + g), ctx->h2d));
@@ -1142,7 +1265,10 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
     const int64_t rows = rows_of(i);
     const int64_t p_sr = cn.p_sk == 1 ? K : 1, p_sk = cn.p_sk == 1 ? 1 : rows;
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_UP + g), 0));
-    if (used[g]) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_DOWN + g), 0));
+    if (used[g]) {
+      d2h_fence(ctx, down_ticket[g]);
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_DOWN + g), 0));
+    }
     if (tensor) {
       BOF_TRY(launch_split_planes(ctx, ctx->compute, rows, K, praw[g], p_sr, p_sk, p_hi_of(g), p_lo_of(g), kp));
       BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_SPLIT + g), ctx->compute));
@@ -1179,10 +1305,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   auto fetch_block = [&](int i) -> int {
     const int g = i % NB;
     const int64_t r0 = (int64_t)i * rb, rows = std::min(cn.Mo, r0 + rb) - r0;
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_DONE + g), 0));
-    BOF_TRY(copy2d(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk_of(g), (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
-    trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
+    BOF_TRY(d2h_transfer(ctx, c + r0 * cn.ldc, (size_t)cn.ldc * 4, cblk_of(g), (size_t)cn.No * 4, (size_t)cn.No * 4, (size_t)rows,
+                         ctx->d2h, get_event(ctx, EV_DONE + g), get_event(ctx, EV_DOWN + g), &down_ticket[g]));
+    if (down_ticket[g] == 0) trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
     return BOF_OK;
   };
 
@@ -1223,14 +1348,15 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // seen with BOF_TRACE=1) before it could reuse generation 0.
   const int npro = n_qpan > 1 ? std::min({nblk, NB - 1, n_qpan}) : 1;  // blocks handled by the prologue
   auto pan = [&](int j, int64_t* n0, int64_t* n1) { *n0 = (int64_t)j * qpan_rows; *n1 = std::min(cn.No, *n0 + qpan_rows); };
-  for (int t = 0; t < n_qpan; ++t) {
-    BOF_TRY(upload_q_panel(t));
-    if (t < npro) BOF_TRY(upload_block(t));
-  }
   const bool merge = tensor;  // the CUDA-core path multiplies one block per launch
+  // Uploads and launches are issued panel by panel: with pinned memory the order of issue is immaterial (everything
+  // is asynchronous), but a pageable upload blocks this thread while it is staged, and launching only after the
+  // whole prologue had been uploaded left the GPU idle for the first 170 ms at 32768^3 (BOF_TRACE).
   for (int t = 0; t < n_qpan; ++t) {
     int64_t n0, n1;
     pan(t, &n0, &n1);
+    BOF_TRY(upload_q_panel(t));
+    if (t < npro) BOF_TRY(upload_block(t));
     BOF_TRY(split_q_panel(t));
     // panel t against the blocks that landed before it: one launch over those consecutive generations
     const int older = std::min(t, npro);
@@ -1269,13 +1395,12 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
           BOF_TRY(launch_add_outer_terms(ctx, ctx->compute, cblk_of(g) + n0, rows, n1 - n0, cn.No, term_rows_d + r0,
                                          term_cols_d + n0, canon_rows_are_m ? 1 : 0));
         BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->compute));
-        BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, EV_QPAN + j), 0));
-        BOF_TRY(copy2d(ctx, c + r0 * cn.ldc + n0, (size_t)cn.ldc * 4, cblk_of(g) + n0, (size_t)cn.No * 4, (size_t)(n1 - n0) * 4,
-                       (size_t)rows, D2H, ctx->d2h));
-        trace_mark(ctx, ctx->d2h, "d2h: last block, slab downloaded", j);
+        BOF_TRY(d2h_transfer(ctx, c + r0 * cn.ldc + n0, (size_t)cn.ldc * 4, cblk_of(g) + n0, (size_t)cn.No * 4, (size_t)(n1 - n0) * 4,
+                             (size_t)rows, ctx->d2h, get_event(ctx, EV_QPAN + j), n1 == cn.No ? get_event(ctx, EV_DOWN + g) : nullptr,
+                             &down_ticket[g]));
+        if (down_ticket[g] == 0) trace_mark(ctx, ctx->d2h, "d2h: last block, slab downloaded", j);
       }
       BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DONE + g), ctx->compute));
-      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_DOWN + g), ctx->d2h));
       used[g] = true;
       fetch_end = i;
       break;
@@ -1578,6 +1703,7 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
   }
   // events: 0+gp panel uploaded, 2+gp panel consumed, 4+g old C block uploaded, 6+g block computed, 8+g block downloaded
   bool pan_used[2] = {false, false}, blk_used[2] = {false, false};
+  uint64_t down_ticket[2] = {0, 0};  // pageable C: the drainer enqueues the download and records event 8+g
   auto upload_panel = [&](int p) -> int {
     const int gp = p & 1;
     const int64_t j0 = (int64_t)p * kb, kbp = std::min(kb, k - j0);
@@ -1605,6 +1731,7 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
     const int64_t z0 = oh[r0] - oh[0];
     float* bp = bpan_all + (size_t)gp * pan_elems;
     float* c_io = colmaj ? cblk_t[g] : cblk[g];
+    if (blk_used[g]) d2h_fence(ctx, down_ticket[g]);  // event 8+g recorded, 6+g may be re-recorded
     if (beta != 0.f) {
       if (blk_used[g]) {
         BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, get_event(ctx, 6 + g), 0));
@@ -1636,11 +1763,11 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
     const int64_t j0 = (int64_t)p * kb, kbp = std::min(kb, k - j0);
     const int64_t r0 = (int64_t)i * rows_blk, rows = std::min(rows_blk, out_rows - r0);
     float* c_io = colmaj ? cblk_t[g] : cblk[g];
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, get_event(ctx, 6 + g), 0));
-    if (colmaj) BOF_TRY(copy2d(ctx, c + j0 * out_rows + r0, (size_t)out_rows * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)kbp, D2H, ctx->d2h));
-    else if (npan == 1) BOF_TRY(copy1d(ctx, c + r0 * k, c_io, (size_t)rows * k * 4, D2H, ctx->d2h));
-    else BOF_TRY(copy2d(ctx, c + r0 * k + j0, (size_t)k * 4, c_io, (size_t)kbp * 4, (size_t)kbp * 4, (size_t)rows, D2H, ctx->d2h));
-    BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, 8 + g), ctx->d2h));
+    cudaEvent_t ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
+    uint64_t* tk = &down_ticket[g];
+    if (colmaj) BOF_TRY(d2h_transfer(ctx, c + j0 * out_rows + r0, (size_t)out_rows * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)kbp, ctx->d2h, ev_done, ev_down, tk));
+    else if (npan == 1) BOF_TRY(d2h_transfer(ctx, c + r0 * k, (size_t)rows * k * 4, c_io, (size_t)rows * k * 4, (size_t)rows * k * 4, 1, ctx->d2h, ev_done, ev_down, tk));
+    else BOF_TRY(d2h_transfer(ctx, c + r0 * k + j0, (size_t)k * 4, c_io, (size_t)kbp * 4, (size_t)kbp * 4, (size_t)rows, ctx->d2h, ev_done, ev_down, tk));
     return BOF_OK;
   };
   // software pipeline over (panel, block): launch step s, then download step s-1
@@ -1787,8 +1914,7 @@ int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host) {
     BOF_TRY(launch_idx_widen(ctx, s, km->assign, km->assign64, km->npoints));
     BOF_TRY(copy1d(ctx, assign_host, km->assign64, (size_t)km->npoints * 8, cudaMemcpyDeviceToHost, s));
   }
-  BOF_CUDA(ctx, cudaStreamSynchronize(s));
-  BOF_TRY(drain_wait(ctx));
+  BOF_TRY(sync_all(ctx));
   return call_guard.done();
 }
 

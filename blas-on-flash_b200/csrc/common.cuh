@@ -63,6 +63,10 @@ struct bof_ctx {
   struct TraceMark { cudaEvent_t ev; const char* what; int idx; };
   std::vector<TraceMark> trace;
   std::vector<cudaEvent_t> trace_pool;
+  struct HostMark { double ms; const char* what; long idx; };
+  std::vector<HostMark> host_trace;   // wall-clock marks of the calling and the drainer thread
+  std::mutex host_trace_mu;
+  double trace_t0 = 0.0;
   // CUDA-event bracket of the most recent tensor-core GEMM kernel (for the roofline figure)
   cudaEvent_t tk0 = nullptr, tk1 = nullptr;
   bool tk_valid = false;

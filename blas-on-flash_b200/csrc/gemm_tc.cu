@@ -845,10 +845,16 @@ int launch_gemm_tc(bof_ctx* ctx, cudaStream_t s, int cta_group, int64_t M, int64
     const size_t waves = (size_t)ceil_div(num_items, clusters);
     const size_t n_ctr = waves * (size_t)ceil_div(prm.num_kb, prm.sync_kb);
     if (ctx->sync_ctr_count < n_ctr) {
+      // Sized with headroom on first use: cudaFree / cudaMalloc synchronise the whole device, and in the middle of
+      // a host pipeline (the first full-width block after narrower prologue launches) that stalled the caller for
+      // as long as the drainer thread kept device->host copies in flight (BOF_TRACE: 0.9 s at 32768^3).
+      size_t n_alloc = 1u << 16;
+      while (n_alloc < n_ctr) n_alloc <<= 1;
       if (ctx->sync_ctr) BOF_CUDA(ctx, cudaFree(ctx->sync_ctr));
       ctx->sync_ctr = nullptr;
-      BOF_CUDA(ctx, cudaMalloc(&ctx->sync_ctr, n_ctr * sizeof(uint32_t)));
-      ctx->sync_ctr_count = n_ctr;
+      ctx->sync_ctr_count = 0;
+      BOF_CUDA(ctx, cudaMalloc(&ctx->sync_ctr, n_alloc * sizeof(uint32_t)));
+      ctx->sync_ctr_count = n_alloc;
     }
     BOF_CUDA(ctx, cudaMemsetAsync(ctx->sync_ctr, 0, n_ctr * sizeof(uint32_t), s));
     prm.sync_counters = ctx->sync_ctr;
