@@ -4,6 +4,7 @@
 // the reference's scheduler / cache / io_executor / file_handle stack (src/scheduler/*.cpp, src/file_handles/*.cpp).
 #include "host_internal.cuh"
 
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -330,6 +331,22 @@ bool file_xfer(bool write, int fd, char* buf, size_t len, uint64_t off) {
 }
 
 // rows x width bytes between a pitched host matrix and a tightly packed staging slot, split over the pool
+#ifndef MADV_POPULATE_READ
+#define MADV_POPULATE_READ 22
+#define MADV_POPULATE_WRITE 23
+#endif
+// Map the pages of a host range in one kernel call before touching them: a freshly mmap'd file (the flash_ptr
+// case) otherwise takes one minor fault per 4 KiB page inside the memcpy.  Opt-in (BOF_POPULATE=1): the A/B on
+// /dev/shm files was mixed (profiles/r01/populate_ab.txt: gemm 0.83 -> 0.60 s, csrmm 1.08 -> 1.35 s, single runs).
+void populate_range(char* p, size_t len, bool for_write) {
+  static const bool on = getenv("BOF_POPULATE") && atoi(getenv("BOF_POPULATE")) != 0;
+  static const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+  if (!on || len < (64u << 10)) return;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(page - 1);
+  const uintptr_t b = (reinterpret_cast<uintptr_t>(p) + len + page - 1) & ~(page - 1);
+  (void)madvise(reinterpret_cast<void*>(a), b - a, for_write ? MADV_POPULATE_WRITE : MADV_POPULATE_READ);  // best effort
+}
+
 void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_t width, size_t rows, bool to_packed) {
   const double t0 = now_ms();
   const size_t total = width * rows;
@@ -348,10 +365,13 @@ void host_rows_copy(bof_ctx* ctx, char* packed, char* host, size_t hpitch, size_
     if (hpitch == width) {  // flat: split by bytes
       const size_t b0 = total * part / parts, b1 = total * (part + 1) / parts;
       if (via_fd && file_xfer(!to_packed, fd, packed + b0, b1 - b0, foff + b0)) return;
+      populate_range(host + b0, b1 - b0, !to_packed);
       if (to_packed) std::memcpy(packed + b0, host + b0, b1 - b0);
       else std::memcpy(host + b0, packed + b0, b1 - b0);
     } else {
       const size_t r0 = rows * part / parts, r1 = rows * (part + 1) / parts;
+      if (!via_fd && r1 > r0 && width * 2 >= hpitch)  // dense enough that most pages of the span are touched
+        populate_range(host + r0 * hpitch, (r1 - r0 - 1) * hpitch + width, !to_packed);
       for (size_t r = r0; r < r1; ++r) {
         if (via_fd && file_xfer(!to_packed, fd, packed + r * width, width, foff + r * hpitch)) continue;
         if (to_packed) std::memcpy(packed + r * width, host + r * hpitch, width);
