@@ -120,7 +120,7 @@ int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n,
   if (m == 0 || k == 0) return BOF_OK;
   if (ord == 'R') {
     BOF_REQUIRE(ctx, ldb >= k && ldc >= k, "csrmm: leading dimension too small");
-    return launch_spmm_rm(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+    return launch_spmm_rm(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc, n);
   }
   // Column-major B (n x k, ldb >= n) and C (m x k, ldc >= m): transpose-on-stage around the
   // row-major kernel; the gathers need B rows contiguous.
@@ -131,7 +131,7 @@ int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n,
   float* Bt = reinterpret_cast<float*>(base);
   float* Ct = reinterpret_cast<float*>(base + round_up<size_t>((size_t)n * k * 4, 256));
   BOF_TRY(launch_transpose(ctx, s, k, n, B, ldb, Bt, k));
-  BOF_TRY(launch_spmm_rm(ctx, s, m, k, 1.f, vals, idx, offs, Bt, k, 0.f, Ct, k));
+  BOF_TRY(launch_spmm_rm(ctx, s, m, k, 1.f, vals, idx, offs, Bt, k, 0.f, Ct, k, n));
   return launch_transpose_axpby(ctx, s, m, k, alpha, Ct, k, beta, C, ldc);
 }
 

@@ -132,9 +132,11 @@ int slot_reserve(bof_ctx* ctx, int slot, size_t count, T** out) {
 
 // ---- kernel launchers implemented in the .cu files (device pointers, no validation) --------
 
+// b_rows = number of rows of B (the gather target) when the caller knows it, 0 otherwise: it only steers the
+// choice between kernel variants (L2 residency of the gather target).
 int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                    const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
-                   int64_t ldb, float beta, float* C, int64_t ldc);
+                   int64_t ldb, float beta, float* C, int64_t ldc, int64_t b_rows = 0);
 int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
                 const int32_t* idx, const int64_t* offs, const float* x, float* y);
 int launch_idx_narrow(bof_ctx* ctx, cudaStream_t s, const int64_t* in, int32_t* out, int64_t n);

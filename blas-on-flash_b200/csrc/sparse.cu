@@ -443,7 +443,7 @@ int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float al
 
 int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                    const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
-                   int64_t ldb, float beta, float* C, int64_t ldc) {
+                   int64_t ldb, float beta, float* C, int64_t ldc, int64_t b_rows) {
   if (m == 0 || k == 0) return BOF_OK;
   const bool vec_ok =
       (k % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) && aligned16(B) && aligned16(C);
@@ -471,7 +471,20 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
     return (k <= 128) ? spmm_tma_launch<1, 4>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
                       : spmm_tma_launch<2, 8>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
   if (k <= 128) {
+    // B larger than L2 can hold next to the A stream, but a 64-column half of it fits: gather from one half at a
+    // time (cfg-1: B = 134 MB against 126 MB of L2; 0.675 -> 0.602 ms, profiles/r01/spmm_variants.txt).  For a B
+    // far beyond L2 (cfg-3) the halves do not fit either and the second pass over A would only cost.
+    if (variant < 0 && b_rows > 0) {
+      const double l2 = (double)ctx->l2_bytes, b_bytes = (double)b_rows * ldb * 4, half = (double)b_rows * 64 * 4;
+      if (b_bytes > 0.5 * l2 && half <= 0.7 * l2 && ldb == k) BOF_SPMM_V(16, 1, 8, 4);
+    }
     switch (variant) {
+      // 64-column chunks (grid.y = 2, all row blocks of chunk 0 are scheduled before chunk 1): half of B at a time
+      // is the gather target, which fits L2 when the whole B does not
+      case 8: BOF_SPMM_V(16, 1, 8, 4);
+      case 9: BOF_SPMM_V(16, 1, 4, 4);
+      case 10: BOF_SPMM_V(16, 1, 16, 2);
+      case 11: BOF_SPMM_V(16, 1, 16, 3);
       case 1: BOF_SPMM_V(32, 1, 4, 5);
       case 2: BOF_SPMM_V(32, 1, 4, 6);
       case 3: BOF_SPMM_V(32, 1, 8, 3);

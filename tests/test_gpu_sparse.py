@@ -170,9 +170,10 @@ def test_host_csrmm_empty(ctx):
     ctx.host_csrmm("N", 0, 5, 3, 1.0, 0.0, e, ia, np.zeros(0, np.int64), "R", np.zeros((5, 3), np.float32), e)
 
 
-@pytest.mark.parametrize("variant", ["6", "3"])
+@pytest.mark.parametrize("variant", ["6", "3", "8"])
 def test_spmm_kernel_variants_child_process(variant):
-    """BOF_SPMM_VARIANT=6 selects the TMA-staged A-stream kernel (cp.async.bulk + mbarrier); 3 is a register variant."""
+    """BOF_SPMM_VARIANT=6 selects the TMA-staged A-stream kernel (cp.async.bulk + mbarrier); 3 is a register variant;
+    8 is the 64-column-chunk kernel the default policy picks when half of B fits L2 but all of it does not."""
     import os, subprocess, sys
     script = Path(__file__).parent / "spmm_variant_check.py"
     r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, BOF_SPMM_VARIANT=variant),
@@ -192,3 +193,17 @@ def test_failed_call_leaves_the_context_usable(bof, ctx):
     assert "failed" in ctx.last_error().lower() or "memory" in ctx.last_error().lower()
     ctx.host_csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, C)
     assert oracle.rel_fro(C, oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32), acc64=True)) <= TOL
+
+
+def test_spmm_l2_half_policy_shape(ctx):
+    """B of 72 MB (more than half of L2, a 64-column half fits): the launcher gathers from one half of B at a time."""
+    rng = np.random.default_rng(23)
+    m, n, k = 4096, 140_000, 128
+    a, ia, ja = ragged_csr(rng, m, n, 30)
+    B = rng.random((n, k), dtype=np.float32)
+    C0 = rng.random((m, k), dtype=np.float32)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    Cd = dev(C0)
+    ctx.spmm("R", m, n, k, 1.5, vals, idx, offs, dev(B), k, 0.5, Cd, k)
+    ref = oracle.csrmm("N", m, n, k, 1.5, 0.5, a, ia, ja, "R", B, C0, acc64=True)
+    assert oracle.rel_fro(Cd.cpu().numpy(), ref) <= TOL

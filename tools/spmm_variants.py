@@ -11,7 +11,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     bof = g.load_package(); ctx = bof.Context(device=0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = {"variant": int(os.environ.get("BOF_SPMM_VARIANT", "0"))}
-    for name, m, nzr, k in (("cfg1", 262144, 64, 128), ("cfg3_slice", 1 << 21, 100, 256)):
+    cases = (("cfg1", 262144, 64, 128),) if os.environ.get("ONLY_CFG1") else (("cfg1", 262144, 64, 128), ("cfg3_slice", 1 << 21, 100, 256))
+    for name, m, nzr, k in cases:
         vals, idx, offs = gen_csr_gpu(m, m, nzr, 1)
         B = torch.rand((m, k), device="cuda"); C = torch.empty((m, k), device="cuda")
         t, tmin = time_gpu(lambda: ctx.spmm("R", m, m, k, 1.0, vals, idx, offs, B, k, 0.0, C, k), flush=flush)
@@ -20,7 +21,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         del vals, idx, offs, B, C
     print(json.dumps(out), flush=True)
 else:
-    for v in range(8):
+    for v in (list(range(8)) if len(sys.argv) < 2 else [int(x) for x in sys.argv[1].split(',')]):
         env = dict(os.environ, BOF_SPMM_VARIANT=str(v))
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)
