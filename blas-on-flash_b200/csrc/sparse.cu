@@ -470,14 +470,13 @@ int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alp
   if (variant == 7 && k > 64)
     return (k <= 128) ? spmm_tma_launch<1, 4>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc)
                       : spmm_tma_launch<2, 8>(ctx, s, m, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc);
+  // B larger than L2 can hold next to the A stream, but a 64-column slice of it fits: gather from one slice at a
+  // time (cfg-1: B = 134 MB against 126 MB of L2; 0.675 -> 0.602 ms, profiles/r01/spmm_variants.txt).  For a B
+  // far beyond L2 (cfg-3) the slices do not fit either and the extra passes over A would only cost.
+  const bool l2_slices = b_rows > 0 && ldb == k && (double)b_rows * ldb * 4 > 0.5 * (double)ctx->l2_bytes &&
+                         (double)b_rows * 64 * 4 <= 0.7 * (double)ctx->l2_bytes;
+  if ((variant < 0 && l2_slices) || variant == 12) BOF_SPMM_V(16, 1, 8, 4);
   if (k <= 128) {
-    // B larger than L2 can hold next to the A stream, but a 64-column half of it fits: gather from one half at a
-    // time (cfg-1: B = 134 MB against 126 MB of L2; 0.675 -> 0.602 ms, profiles/r01/spmm_variants.txt).  For a B
-    // far beyond L2 (cfg-3) the halves do not fit either and the second pass over A would only cost.
-    if (variant < 0 && b_rows > 0) {
-      const double l2 = (double)ctx->l2_bytes, b_bytes = (double)b_rows * ldb * 4, half = (double)b_rows * 64 * 4;
-      if (b_bytes > 0.5 * l2 && half <= 0.7 * l2 && ldb == k) BOF_SPMM_V(16, 1, 8, 4);
-    }
     switch (variant) {
       // 64-column chunks (grid.y = 2, all row blocks of chunk 0 are scheduled before chunk 1): half of B at a time
       // is the gather target, which fits L2 when the whole B does not

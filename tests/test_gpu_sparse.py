@@ -195,10 +195,12 @@ def test_failed_call_leaves_the_context_usable(bof, ctx):
     assert oracle.rel_fro(C, oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32), acc64=True)) <= TOL
 
 
-def test_spmm_l2_half_policy_shape(ctx):
-    """B of 72 MB (more than half of L2, a 64-column half fits): the launcher gathers from one half of B at a time."""
+@pytest.mark.parametrize("k", [128, 200, 256])
+def test_spmm_l2_half_policy_shape(ctx, k):
+    """B of 72-143 MB (more than half of L2, a 64-column slice fits): the launcher gathers from one slice of B at a time
+    (16-lane row groups, ceil(k/64) column chunks)."""
     rng = np.random.default_rng(23)
-    m, n, k = 4096, 140_000, 128
+    m, n = 4096, 140_000
     a, ia, ja = ragged_csr(rng, m, n, 30)
     B = rng.random((n, k), dtype=np.float32)
     C0 = rng.random((m, k), dtype=np.float32)

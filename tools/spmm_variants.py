@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     bof = g.load_package(); ctx = bof.Context(device=0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     out = {"variant": int(os.environ.get("BOF_SPMM_VARIANT", "0"))}
-    cases = (("cfg1", 262144, 64, 128),) if os.environ.get("ONLY_CFG1") else (("cfg1", 262144, 64, 128), ("cfg3_slice", 1 << 21, 100, 256))
+    cases = (("cfg1", 262144, 64, int(os.environ.get("SPMM_K", "128"))),) if os.environ.get("ONLY_CFG1") else (("cfg1", 262144, 64, 128), ("cfg3_slice", 1 << 21, 100, 256))
     for name, m, nzr, k in cases:
         vals, idx, offs = gen_csr_gpu(m, m, nzr, 1)
         B = torch.rand((m, k), device="cuda"); C = torch.empty((m, k), device="cuda")
