@@ -31,6 +31,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* Every entry point is exported explicitly; the library itself is built with -fvisibility=hidden so that nothing
+ * but this ABI leaves it. */
+#if defined(__GNUC__)
+#define BOF_API __attribute__((visibility("default")))
+#else
+#define BOF_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -79,23 +87,23 @@ typedef struct bof_stats {
 /* ---- 1. context ----------------------------------------------------------------------- */
 
 /* Replaces the static `flash::sched` + flash_setup() (src/lib_funcs.cpp:9,18-23). */
-int bof_ctx_create(const bof_config* cfg, bof_ctx** out);
-int bof_ctx_destroy(bof_ctx* ctx);
+BOF_API int bof_ctx_create(const bof_config* cfg, bof_ctx** out);
+BOF_API int bof_ctx_destroy(bof_ctx* ctx);
 /* Message of the last failure on this context (ctx may be NULL: last failure of ctx creation). */
-const char* bof_last_error(const bof_ctx* ctx);
-int bof_get_stats(const bof_ctx* ctx, bof_stats* out);
+BOF_API const char* bof_last_error(const bof_ctx* ctx);
+BOF_API int bof_get_stats(const bof_ctx* ctx, bof_stats* out);
 /* Total kernels launched by this context since creation (bench.py's gpu_launches). */
-int64_t bof_launch_count(const bof_ctx* ctx);
+BOF_API int64_t bof_launch_count(const bof_ctx* ctx);
 /* Tell the library that host range [base, base+len) is the mmap of descriptor `fd` starting at byte
  * `file_offset` (what map_file() creates, include/pointers/allocator.h:19-45).  With BOF_STAGE_FD=1 in the
  * environment host entry points move such operands with pread/pwrite into their pinned staging buffers --
  * the reference's FlashFileHandle::read/write into cache buffers (src/file_handles/flash_file_handle.cpp:
  * 247-407) -- which pays off for cold files on real disks; by default they copy through the mapping, the
  * faster way for page-cache-resident files (measured).  Process-wide; include/pointers/allocator.h calls it. */
-int bof_register_mapping(const void* base, size_t len, int fd, uint64_t file_offset);
-int bof_unregister_mapping(const void* base);
+BOF_API int bof_register_mapping(const void* base, size_t len, int fd, uint64_t file_offset);
+BOF_API int bof_unregister_mapping(const void* base);
 /* ABI version, bumped on any signature change. */
-int bof_abi_version(void);
+BOF_API int bof_abi_version(void);
 
 /* ---- 2. device-tile kernels ------------------------------------------------------------ */
 
@@ -106,49 +114,49 @@ int bof_abi_version(void);
  * beta == 0 => C is not read (csrmm_task.h:194-196).  `offs` may be un-rebased (offs[0] != 0):
  * vals/idx are indexed by offs[i] - offs[0].  ord='C' needs workspace
  * bof_spmm_workspace_bytes(); ord='R' needs none. */
-int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n, int64_t k,
+BOF_API int bof_spmm_csr_f32(bof_ctx* ctx, void* stream, char ord, int64_t m, int64_t n, int64_t k,
                      float alpha, const float* vals, const int32_t* idx, const int64_t* offs,
                      const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
                      void* workspace, size_t workspace_bytes);
-size_t bof_spmm_workspace_bytes(char ord, int64_t m, int64_t n, int64_t k);
+BOF_API size_t bof_spmm_workspace_bytes(char ord, int64_t m, int64_t n, int64_t k);
 
 /* K4/K5: y = op(A) x, y overwritten (no alpha/beta).
  * Replaces mkl_cspblas_scsrgemv in CsrGemvNoTransInMem::execute
  * (include/tasks/csrgemv_task.h:60-83) and CsrGemvTransInMem::execute (:152-179; the mutex'd
  * `out[i] += v_out[i]` becomes red.global.add.f32).  trans='N': x has n entries, y has m;
  * trans='T': x has m entries, y has n and is zeroed by the call (src/blas/csrgemv.cpp:64). */
-int bof_spmv_csr_f32(bof_ctx* ctx, void* stream, char trans, int64_t m, int64_t n,
+BOF_API int bof_spmv_csr_f32(bof_ctx* ctx, void* stream, char trans, int64_t m, int64_t n,
                      const float* vals, const int32_t* idx, const int64_t* offs, const float* x,
                      float* y);
 
 /* Index staging helpers: int64 (file format, misc/sparse_create.cpp:63-81) <-> int32 (device). */
-int bof_idx_narrow(bof_ctx* ctx, void* stream, const int64_t* in, int32_t* out, int64_t count);
-int bof_idx_widen(bof_ctx* ctx, void* stream, const int32_t* in, int64_t* out, int64_t count);
+BOF_API int bof_idx_narrow(bof_ctx* ctx, void* stream, const int64_t* in, int32_t* out, int64_t count);
+BOF_API int bof_idx_widen(bof_ctx* ctx, void* stream, const int32_t* in, int64_t* out, int64_t count);
 
 /* K3: C = alpha * op(A) * op(B) + beta * C, fp32 in/out, 3xTF32 on tcgen05 tensor cores.
  * Replaces cblas_sgemm in GemmTask::execute (include/tasks/gemm_task.h:67-93); argument meaning
  * as flash::gemm (include/flash_blas.h:14-18): ord 'R'/'C', ta/tb 'N'/'T', ld* = 0 => tight
  * (src/blas/gemm.cpp:63-67).  beta == 0 => C is not read (gemm_task.h:49-53).
  * Needs workspace of bof_sgemm_workspace_bytes(m, n, k) bytes (the TF32 hi/lo operand planes). */
-int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb, int64_t m, int64_t n,
+BOF_API int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb, int64_t m, int64_t n,
                   int64_t k, float alpha, const float* A, int64_t lda, const float* B,
                   int64_t ldb, float beta, float* C, int64_t ldc, void* workspace,
                   size_t workspace_bytes);
-size_t bof_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
+BOF_API size_t bof_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
 /* K6/K7: stable CSR -> CSC (A m x n  ->  A^T as CSR n x m): per output row ascending source
  * row, duplicates in storage order.  Replaces mkl_scsrcsc + index rebase in
  * BlockCsrCscTask::execute (include/tasks/csrcsc_task.h:42-92) and the row-block-ordered merge
  * BlockMergeTask::execute (:136-163).  Atomic-free: radix passes of histogram -> scan -> ranked
  * scatter.  offs/offs_t int64, idx/idx_t int32.  nnz = offs[m] - offs[0] must be < 2^31. */
-int bof_csr2csc(bof_ctx* ctx, void* stream, int64_t m, int64_t n, int64_t nnz,
+BOF_API int bof_csr2csc(bof_ctx* ctx, void* stream, int64_t m, int64_t n, int64_t nnz,
                 const int64_t* offs, const int32_t* idx, const float* vals, int64_t* offs_t,
                 int32_t* idx_t, float* vals_t, void* workspace, size_t workspace_bytes);
-size_t bof_csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz);
+BOF_API size_t bof_csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz);
 
 /* K11: out[r] = sum_j X[r, j]^2 for a row-major rows x dim matrix.
  * Replaces the cblas_sdot loops of drivers/in_mem_kmeans.cpp:75-78,179-182. */
-int bof_row_sqnorm_f32(bof_ctx* ctx, void* stream, int64_t rows, int64_t dim, const float* X,
+BOF_API int bof_row_sqnorm_f32(bof_ctx* ctx, void* stream, int64_t rows, int64_t dim, const float* X,
                        int64_t ldx, float* out);
 
 /* K8+K9: assign[p] = first c minimising | fl(fl(-2 <x_p, mu_c> + c_l2sq[c]) + p_l2sq[p]) |.
@@ -158,14 +166,14 @@ int bof_row_sqnorm_f32(bof_ctx* ctx, void* stream, int64_t rows, int64_t dim, co
  * Needs workspace bof_kmeans_workspace_bytes(). `points_planes` is optional: a caller iterating
  * on the same points passes the buffer filled by bof_kmeans_prepare_points() to skip the
  * per-call TF32 split of the points. */
-int bof_kmeans_assign(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+BOF_API int bof_kmeans_assign(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
                       const float* points, const float* centers, const float* c_l2sq,
                       const float* p_l2sq, int32_t* assign, const void* points_planes,
                       void* workspace, size_t workspace_bytes);
-size_t bof_kmeans_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim,
+BOF_API size_t bof_kmeans_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim,
                                   int with_point_planes);
-size_t bof_kmeans_point_planes_bytes(int64_t npoints, int64_t dim);
-int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64_t dim,
+BOF_API size_t bof_kmeans_point_planes_bytes(int64_t npoints, int64_t dim);
+BOF_API int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64_t dim,
                               const float* points, void* points_planes);
 
 /* K10: sums[c, :] = sum_{p: assign[p]==c} x_p, added sequentially in ascending p (point ids are
@@ -174,25 +182,25 @@ int bof_kmeans_prepare_points(bof_ctx* ctx, void* stream, int64_t npoints, int64
  * drivers/in_mem_kmeans.cpp:105-125.  sums is K x dim fp32 followed by nothing; counts K fp32
  * (exact below 2^24 points per cluster and NCCL-allreduce friendly).  The caller all-reduces
  * [sums | counts] across GPUs and then calls bof_kmeans_finalize. */
-int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
+BOF_API int bof_kmeans_reduce(bof_ctx* ctx, void* stream, int64_t npoints, int64_t ncenters, int64_t dim,
                       const float* points, const int32_t* assign, float* sums, float* counts,
                       void* workspace, size_t workspace_bytes);
-size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim);
+BOF_API size_t bof_kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim);
 /* centers[c] = sums[c] / counts[c], empty cluster => zero vector (in_mem_kmeans.cpp:112);
  * also refreshes c_l2sq[c] (in_mem_kmeans.cpp:75-78). */
-int bof_kmeans_finalize(bof_ctx* ctx, void* stream, int64_t ncenters, int64_t dim,
+BOF_API int bof_kmeans_finalize(bof_ctx* ctx, void* stream, int64_t ncenters, int64_t dim,
                         const float* sums, const float* counts, float* centers, float* c_l2sq);
 
 /* ---- 3. host entry points (what include/flash_blas.h's adapters call) -------------------- */
 
 /* flash::csrmm (include/flash_blas.h:37-46; src/blas/csrmm.cpp:424-472).  a/ja are indexed
  * from ia[0]; ja/ia int64 as on disk.  trans_a='T' is csr2csc followed by 'N'. */
-int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha,
+BOF_API int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha,
                    float beta, const float* a, const int64_t* ia, const int64_t* ja, char ord_b,
                    const float* b, float* c);
 
 /* flash::gemm (include/flash_blas.h:14-18; src/blas/gemm.cpp:27-202). */
-int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
+BOF_API int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k,
                   float alpha, float beta, const float* a, const float* b, float* c, int64_t lda,
                   int64_t ldb, int64_t ldc);
 
@@ -200,10 +208,10 @@ int bof_host_gemm(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n
  * HBM: every rank uploads only 1/G of B and the ranks all-gather the rest over NVLink
  * (ncclAllGather, or blas-on-flash_b200/dist.py::allgather_dense); only the sharded operand and the
  * output rows cross PCIe.  b_dev is read-only.  Row-major, csrmm trans_a='N' only. */
-int bof_host_gemm_devb(bof_ctx* ctx, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
+BOF_API int bof_host_gemm_devb(bof_ctx* ctx, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
                        float beta, const float* a, const float* b_dev, float* c, int64_t lda,
                        int64_t ldb, int64_t ldc);
-int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alpha, float beta,
+BOF_API int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alpha, float beta,
                         const float* a, const int64_t* ia, const int64_t* ja, const float* b_dev,
                         float* c);
 
@@ -211,17 +219,17 @@ int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alp
  * include/tasks/kmeans_task.h:53-82): the product of bof_host_gemm, then C(i, j) += c_l2sq[i] and
  * C(i, j) += p_l2sq[j] in that order (i over m, j over n), applied to each output block on the device
  * before it is downloaded.  c_l2sq (m entries) and p_l2sq (n entries) are host arrays. */
-int bof_host_kmeans_dist(bof_ctx* ctx, char mat_ord, char trans_a, char trans_b, int64_t m, int64_t n,
+BOF_API int bof_host_kmeans_dist(bof_ctx* ctx, char mat_ord, char trans_a, char trans_b, int64_t m, int64_t n,
                          int64_t k, float alpha, float beta, const float* a, const float* b, float* c,
                          int64_t lda_a, int64_t lda_b, int64_t lda_c, const float* c_l2sq,
                          const float* p_l2sq);
 
 /* flash::csrgemv (include/flash_blas.h:55-57; src/blas/csrgemv.cpp:82-97). */
-int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a,
+BOF_API int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const float* a,
                      const int64_t* ia, const int64_t* ja, const float* b, float* c);
 
 /* flash::csrcsc (include/flash_blas.h:49-52; src/blas/csrcsc.cpp:32-159). */
-int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const int64_t* ja,
+BOF_API int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const int64_t* ja,
                     const float* a, int64_t* ia_tr, int64_t* ja_tr, float* a_tr);
 
 /* A resident in HBM across calls: the in-memory-B/C csrmm overload and csrgemv as the inner
@@ -236,15 +244,15 @@ int bof_host_csrcsc(bof_ctx* ctx, int64_t m, int64_t n, const int64_t* ia, const
  * callers that keep B and C on the device and call bof_spmm_csr_f32 / bof_spmv_csr_f32 themselves.
  * One call at a time per context, like every other entry point. */
 typedef struct bof_csr bof_csr;
-int bof_csr_open(bof_ctx* ctx, int64_t m, int64_t n, const float* a, const int64_t* ia, const int64_t* ja,
+BOF_API int bof_csr_open(bof_ctx* ctx, int64_t m, int64_t n, const float* a, const int64_t* ia, const int64_t* ja,
                  bof_csr** out);
-int bof_csr_build_transpose(bof_csr* h);
-int bof_csr_arrays(bof_csr* h, char trans_a, const float** vals, const int32_t** idx, const int64_t** offs,
+BOF_API int bof_csr_build_transpose(bof_csr* h);
+BOF_API int bof_csr_arrays(bof_csr* h, char trans_a, const float** vals, const int32_t** idx, const int64_t** offs,
                    int64_t* nnz);
-int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, char ord_b, const float* b,
+BOF_API int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, char ord_b, const float* b,
                float* c);
-int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y);
-int bof_csr_close(bof_csr* h);
+BOF_API int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y);
+BOF_API int bof_csr_close(bof_csr* h);
 
 /* One Lloyd iteration on this rank's shard of the points, device-resident across calls:
  * bof_kmeans_open uploads the shard once (drivers/kmeans.cpp:206-217: points mapped, norms
@@ -254,13 +262,13 @@ int bof_csr_close(bof_csr* h);
  * collective on the path); bof_kmeans_update divides and refreshes the resident centers.
  * assign_out (host, int64 as FBLAS_UINT center_index, in_mem_kmeans.cpp:82-85) may be NULL. */
 typedef struct bof_kmeans bof_kmeans;
-int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim,
+BOF_API int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim,
                     const float* points_host, const float* centers_host, bof_kmeans** out);
-int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_floats);
-int bof_kmeans_update(bof_kmeans* km);
-int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host);
-void* bof_kmeans_stream(bof_kmeans* km);
-int bof_kmeans_close(bof_kmeans* km);
+BOF_API int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_floats);
+BOF_API int bof_kmeans_update(bof_kmeans* km);
+BOF_API int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host);
+BOF_API void* bof_kmeans_stream(bof_kmeans* km);
+BOF_API int bof_kmeans_close(bof_kmeans* km);
 
 #ifdef __cplusplus
 }
