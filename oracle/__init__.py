@@ -2,7 +2,9 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package; the product path never does.
-PARITY UNPINNED at the MKL boundary -- see the header of ``oracle.c`` and DESIGN.md.
+PARITY PINNED TO THE REFERENCE: tests/golden/golden_ref.npz holds outputs written by the reference's own
+binaries (``oracle/_ref``, unmodified sources built by ``oracle/Makefile.ref``); ``tests/test_oracle_ref.py``
+checks every function here against them and against live runs of those binaries (``oracle/ref_run.py``).
 """
 from __future__ import annotations
 

@@ -4,14 +4,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this file's library.  The product (libbof_b200.so, include/flash_blas.h) never does.
  *
- * PARITY UNPINNED at the MKL boundary: the reference keeps no golden vectors, known-answer tests
- * or fixtures for this path and cannot be built here (needs mkl.h, ILP64
- * MKL and libaio, none present).  What this file restates is the *documented* semantics of the
- * MKL entry points at the reference's call sites, in plain fp32 (and with fp64 accumulation to
- * bound both sides).  It is cross-checked in tests/ against oneMKL 2024.2 as exported by
- * libtorch_cpu.so (sgemm_, mkl_sparse_s_mm, mkl_sparse_s_mv -- the same library family the
- * reference calls) and against scipy's csr->csc; the integer/compare-only results (csrcsc,
- * isamin assignment) are fully determined without MKL.
+ * PARITY PINNED TO THE REFERENCE.  The reference holds no golden vectors for this path (SURVEY.md
+ * section 8c), so they are produced by running the reference itself: oracle/Makefile.ref compiles its
+ * unmodified sources (in_mem_* drivers and the flash:: library with its scheduler / cache / libaio file
+ * handles) behind two shim headers -- oracle/ref_shim/mkl.h, which forwards to the oneMKL 2024.2 inside
+ * libtorch_cpu.so (SGEMM_64, mkl_sparse_s_mm/_mv) and restates mkl_scsrcsc / BLAS-1, and
+ * oracle/ref_shim/libaio.h over the native-AIO syscalls -- into oracle/_ref/.  tests/golden/golden_ref.npz
+ * holds outputs of those binaries (tests/golden/make_golden_ref.py), and tests/test_oracle_ref.py checks
+ * every function of this file against them and against live runs of the binaries on fresh inputs.
+ * What this file restates is the semantics of the MKL entry points at the reference's call sites, in
+ * plain fp32 (and with fp64 accumulation to bound both sides); the integer/compare-only results
+ * (csrcsc, isamin assignment) are fully determined without MKL.
  *
  * Every function cites the reference file:line it follows (paths relative to the reference tree).
  */
