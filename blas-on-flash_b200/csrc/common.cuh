@@ -76,6 +76,14 @@ struct bof_ctx {
 
 namespace bof {
 
+// cudaFuncSetAttribute applies to the CURRENT device only; one process may hold contexts on several GPUs
+// (bof_config.device), so "already set" is remembered per device ordinal. Setting it twice is harmless.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0; }
+  void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
 inline int fail(bof_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;

@@ -555,6 +555,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
           const float ov = tail->red_val[r_local];
           const int32_t oi = tail->red_idx[r_local];
           if (ov < best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+          // a row whose distances are all NaN / +Inf never updates: keep the result in [0, N) like isamin does
+          if ((uint32_t)best_idx >= (uint32_t)prm.N) best_idx = 0;
           if (row < prm.M) prm.argmin_out[row] = best_idx;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -743,10 +745,10 @@ int make_plane_map(bof_ctx* ctx, CUtensorMap* map, const float* plane, int64_t r
 template <int CG, int EPI, bool CHUNKED, bool HYB>
 int launch_variant(bof_ctx* ctx, cudaStream_t s, const CUtensorMap* maps, const tc::Params& prm, int num_items) {
   auto kern = tc::gemm3xtf32_kernel<CG, EPI, CHUNKED, HYB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(ctx->device)) {
     BOF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    attr_set = true;
+    attr_set.done(ctx->device);
   }
   const int max_clusters = ctx->num_sms / CG;
   const int clusters = std::max(1, std::min(num_items, max_clusters));

@@ -301,8 +301,10 @@ segment_offsets_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, int6
                        OutT* __restrict__ seg_offs) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+    // keys above nseg (never produced by our kernels; a caller-supplied assignment could hold one) must not
+    // run the loop past the (nseg + 1)-entry output
     const int64_t lo = (i == 0) ? 0 : (int64_t)sorted_keys[i - 1] + 1;
-    const int64_t hi = (i == n) ? nseg : (int64_t)sorted_keys[i];
+    const int64_t hi = (i == n) ? nseg : min((int64_t)sorted_keys[i], nseg);
     for (int64_t c = lo; c <= hi; ++c) seg_offs[c] = (OutT)i;
   }
 }
@@ -350,11 +352,11 @@ int radix_pass(bof_ctx* ctx, cudaStream_t s, int64_t n, int shift, const uint32_
   const int64_t tiles = ceil_div<int64_t>(n, RS_TILE);
   const int64_t ncounts = tiles * RS_BINS;
   uint32_t* block_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(counts) + align_up((size_t)ncounts * 4));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need(ctx->device)) {
     BOF_CUDA(ctx, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ScatterSmem)));
-    attr_set = true;
+    attr_set.done(ctx->device);
   }
   radix_hist_kernel<<<(unsigned)tiles, RH_THREADS, 0, s>>>(key_in, n, shift, counts, (unsigned)tiles);
   BOF_LAUNCH_CHECK(ctx, "radix_hist_kernel");
