@@ -28,6 +28,7 @@ class BofConfig(C.Structure):
         ("gemm_force_path", C.c_int32),
         ("gemm_wave_sync", C.c_int32),
         ("gemm_split", C.c_int32),
+        ("radix_max_bits", C.c_int32),
     ]
 
 
