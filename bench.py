@@ -17,9 +17,13 @@ A "step" is one pass of the hot path over that job.
           duration, against 1/(1/TF32 + 2/BF16) (one tf32 and two bf16 MMAs per product), BF16 from
           MEASURED_PEAKS.json, TF32 from a cuBLAS measurement in the same run (sustained figures:
           the kernel runs ~0.2 s per launch).
-  cpu_baseline  MKL sgemm (oneMKL from libtorch_cpu, the library family the reference calls) on
-          the box's host cores on a bounded sample: one 8192^3 GemmTask tile (1/64 of the job).
-  extra   csrmm cfg-1 (configs[0]) device-resident SpMM numbers with the HBM roofline.
+  cpu_baseline  the reference's own in_mem_gemm driver (oracle/_ref, unmodified drivers/in_mem_gemm.cpp ->
+          cblas_sgemm = MKL) on the box's host cores on a bounded sample: one 8192^3 GemmTask tile (1/64 of the
+          job); MKL sgemm through ctypes if the binary is not on the box.
+  extra   every other BASELINE.json config at the same world size (tools/bench_configs.py): csrmm_cfg1,
+          csrmm_cfg3 (sharded; replicated and all-gathered B), csrgemv_N/T_cfg4, csrcsc_cfg4, kmeans_cfg5 (with the
+          NCCL allreduce at N > 1), each with roofline, e2e (host buffers, byte counts), cpu_baseline and a parity
+          figure on the timed buffers; plus the pinned PCIe bandwidth of all ranks copying at once.
 """
 from __future__ import annotations
 
@@ -157,10 +161,40 @@ def gpu_pci_bus_id(torch, local: int):
         return None
 
 
+def ref_gemm_sample(reps: int = 1):
+    """One reference GemmTask tile (8192^3) through the reference's OWN in_mem_gemm driver binary (oracle/_ref,
+    built from the unmodified sources by oracle/Makefile.ref), timed by the driver's own chrono bracket around
+    cblas_sgemm (drivers/in_mem_gemm.cpp:63-70).  Returns (cpu_baseline dict, seconds) or None if the binary is
+    not on this box."""
+    import numpy as np
+    from oracle import ref_run as rr
+
+    if not rr.available():
+        return None
+    n = TILE
+    rng = np.random.default_rng(0)
+    a = rng.random(n * n, dtype=np.float32)
+    b = rng.random(n * n, dtype=np.float32)
+    c = np.zeros(n * n, dtype=np.float32)
+    best = float("inf")
+    for _ in range(reps):
+        _, secs = rr.gemm("R", "N", "N", n, n, n, 1.0, 0.0, a, b, c, n, n, n, want_time=True)
+        if not secs:
+            return None
+        best = min(best, secs)
+    return {"value": 2.0 * n ** 3 / best / 1e9, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "reference",
+            "sample": f"oracle/_ref/in_mem_gemm_driver (unmodified drivers/in_mem_gemm.cpp -> cblas_sgemm, MKL threads = all "
+                      f"{os.cpu_count()} logical cpus) on one reference GemmTask tile {n}^3 = 1/64 of the job, its own timer: {best:.2f} s"}, best
+
+
 def cpu_gemm_sample(reps: int = 2):
-    """MKL sgemm on one reference GemmTask tile (8192^3), all host threads."""
+    """MKL sgemm on one reference GemmTask tile (8192^3), all host threads (fallback when oracle/_ref is absent)."""
     import numpy as np
     from oracle import mkl
+
+    got = ref_gemm_sample(reps=1)
+    if got is not None:
+        return got
 
     n = TILE
     rng = np.random.default_rng(0)
@@ -179,8 +213,8 @@ def cpu_gemm_sample(reps: int = 2):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path for this workload = MKL sgemm on the host cores.
-    The reference itself cannot be built here (needs mkl.h, ILP64 MKL, libaio)."""
+    """--impl reference: the reference's own CPU implementation of this workload -- oracle/_ref/in_mem_gemm_driver,
+    the unmodified reference driver built by oracle/Makefile.ref (MKL sgemm through ctypes when it is absent)."""
     if rank != 0:
         return
     for _ in range(max(args.warmup, 1) - 1):
@@ -198,7 +232,8 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_tile * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "flash::gemm sgemm 32768x32768x32768 fp32 (BASELINE.json configs[1])",
-                   "sample": "each step = one 8192^3 GemmTask tile (1/64 of the job) through MKL sgemm on all host threads"},
+                   "sample": "each step = one 8192^3 GemmTask tile (1/64 of the job) through " + ("the reference's in_mem_gemm driver binary"
+                             if base.get("kind") == "reference" else "MKL sgemm (ctypes)") + " on all host threads"},
         "cpu_baseline": base,
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -237,34 +272,63 @@ def tf32_library_peak(torch, seconds=3.0):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def csrmm_extra(bof, ctx, torch, pk):
-    """configs[0]: in_mem_csrmm 262144^2, 64 nnz/row, k=128 -- device-resident SpMM, HBM roofline."""
-    import numpy as np
-    import oracle
+def run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local):
+    """All other BASELINE.json configs at this world size (collective: every rank takes part)."""
+    from tools import bench_configs as bc
 
-    m = n = 262144
-    k, nzr = 128, 64
-    a, ia, ja = oracle.gen_csr(m, n, nzr, seed=0x5EED0001)
-    vals = torch.from_numpy(a).cuda(); idx = torch.from_numpy(ja.astype(np.int32)).cuda(); offs = torch.from_numpy(ia).cuda()
-    B = torch.rand((n, k), device="cuda"); Cm = torch.empty((m, k), device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    nnz = m * nzr
-    ts = []
-    for i in range(8):
-        flush.zero_()  # evict L2 (126 MB) between iterations
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record(); ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, B, k, 0.0, Cm, k); e1.record()
+    pk2 = dict(pk); pk2["tf32_sustained"] = tf32["sustained"]; pk2["tf32_burst"] = tf32["burst"]
+    env = bc.Env(bof, ctx, rank, world, local, pk2, dist=dist, cpu=not args.no_cpu)
+    want = set(args.extra.split(","))
+    extra = {}
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            r = fn()
+        except Exception as ex:  # the headline must still print
+            import traceback
+            r = {"error": repr(ex)[:300], "trace": traceback.format_exc()[-600:]}
         torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-    t = sum(ts) / len(ts)
-    bytes_gather = nnz * (4 + 4) + (m + 1) * 8 + nnz * k * 4 + m * k * 4
-    bytes_min = nnz * (4 + 4) + (m + 1) * 8 + n * k * 4 + m * k * 4
-    return {"workload": "csrmm 262144^2, 64 nnz/row, k=128 (configs[0]), device-resident, L2 flushed between iterations",
-            "gflops": 2.0 * nnz * k / t / 1e9, "ms": t * 1e3,
-            "roofline": {"bound": "hbm", "achieved": bytes_gather / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": bytes_gather / t / 1e9 / pk["hbm_gbs"], "traffic": None,
-                         "achieved_bytes_min": bytes_min / t / 1e9, "model": "bytes_gather (SURVEY.md 8d)"}}
+        torch.cuda.empty_cache()
+        if isinstance(r, dict):
+            r["bench_seconds"] = round(time.perf_counter() - t0, 1)
+        return r
+
+    if "pcie" in want:
+        extra["pcie"] = guarded("pcie", lambda: bc.pcie_bandwidth(env))
+    if "cfg1" in want:
+        extra["csrmm_cfg1"] = guarded("cfg1", lambda: bc.csrmm_cfg1(env))
+    host_csr = None
+    if "cfg3" in want or "cfg4" in want:
+        t0 = time.perf_counter()
+        try:
+            rec, host_csr = bc.csrmm_cfg3(env, scale=args.scale)
+            rec["bench_seconds"] = round(time.perf_counter() - t0, 1)
+        except Exception as ex:
+            import traceback
+            rec = {"error": repr(ex)[:300], "trace": traceback.format_exc()[-600:]}
+        extra["csrmm_cfg3"] = rec
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+    if "cfg4" in want and host_csr is not None:
+        r = guarded("cfg4", lambda: bc.cfg4(env, host_csr, scale=args.scale))
+        if "error" in r:
+            extra["cfg4"] = r
+        else:
+            r.pop("bench_seconds", None)
+            extra.update(r)
+    host_csr = None
+    if "cfg5" in want:
+        extra["kmeans_cfg5"] = guarded("cfg5", lambda: bc.kmeans_cfg5(env, scale=args.scale))
+    if "pcie" in extra and "h2d_gbs_per_gpu" in extra["pcie"]:
+        # out-of-core legs as multiples of the measured PCIe bound of THIS run (north_star: within 1.3x)
+        h2d = extra["pcie"]["h2d_gbs_per_gpu"]
+        for key in ("csrmm_cfg3", "csrgemv_N_cfg4"):
+            e = extra.get(key, {}).get("e2e")
+            if e and e.get("h2d_bytes_per_step"):
+                bound_ms = e["h2d_bytes_per_step"] / h2d / 1e6
+                e["pcie_h2d_bound_ms"] = bound_ms
+                e["x_of_pcie_bound"] = e["ms"] / bound_ms
+    return extra
 
 
 def main():
@@ -275,6 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=M_FULL, help="override m=n=k (debug only; invalid as a bench value)")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--extra", default="pcie,cfg1,cfg3,cfg4,cfg5", help="which other configs to measure into `extra`")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg-3/4/5 (debug only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on all CPUs (A/B of the NUMA binding)")
     args = ap.parse_args()
@@ -423,12 +489,10 @@ def main():
     e2e["spot_rel_err"] = abs(float(Ch[i0, j0]) - ref0) / abs(ref0)
     del Ah, Bh, Ch, Bdev
 
+    torch.cuda.empty_cache()
     extra = {}
-    if rank == 0 and not args.no_extra:
-        try:
-            extra["csrmm_cfg1"] = csrmm_extra(bof, ctx, torch, pk)
-        except Exception as ex:  # the headline must still print
-            extra["csrmm_cfg1"] = {"error": repr(ex)}
+    if not args.no_extra:
+        extra = run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local)
 
     if rank == 0:
         line = {

@@ -71,8 +71,8 @@ typedef struct bof_config {
                                 hi*hi, all kind::tf32), 2 = hybrid (hi*hi kind::tf32, the two cross
                                 terms on bf16 copies, kind::f16: 2/3 of the tensor time, cross-term
                                 error <= 2^-19 relative)                                          */
-  int32_t radix_max_bits;    /* widest digit of the csrcsc / k-means radix passes: 0 = default 12 (two passes
-                                for up to 2^24 columns); smaller values force more passes (test knob)    */
+  int32_t radix_max_bits;    /* digit width of the csrcsc / k-means radix passes: 0 = default 8; smaller values
+                                force more passes (test knob)                                            */
 } bof_config;
 
 /* Per-stage accounting of the last host entry point, for the out-of-core roofline

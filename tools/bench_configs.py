@@ -1,0 +1,538 @@
+"""Per-config measurements behind ``bench.py``'s ``extra`` object: BASELINE.json configs[0] (csrmm cfg-1),
+configs[2] (csrmm cfg-3 out-of-core), configs[3] (csrgemv + csrcsc, cfg-4) and configs[4] (kmeans cfg-5), at the
+world size bench.py runs under.  Every record carries
+
+  value / ms          device-resident throughput, CUDA events on the launching stream, >= 3 warm-ups, L2 flushed
+                      between iterations when the inputs fit in it, max over ranks
+  roofline            SURVEY.md 8(d) byte / flop model per launch / that time, against MEASURED_PEAKS.json;
+                      ``traffic`` = dram bytes per launch from the committed ncu capture (profiles/r02/), else null
+  e2e                 the same workload through the host entry point the flash:: adapter calls, pinned HOST buffers,
+                      H2D / D2H inside the timed region, with byte counts
+  cpu_baseline        the reference's CPU path on a bounded sample (rank 0, world 1 only): its own in_mem driver
+                      binary (oracle/_ref, kind "reference") or the MKL call it makes (kind "port"), cores stated
+  parity              error of the TIMED buffers against the oracle / MKL / the reference binary
+
+Sharding: csrmm / csrgemv 'N' = output row blocks per rank, dense operand replicated, no collective;
+csrgemv 'T' = partial y per rank, summed on the host in rank order; csrcsc = replicas only; kmeans = points sharded
+and resident, one NCCL allreduce of [K*d sums | K counts] per iteration.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+class Env:
+    def __init__(self, bof, ctx, rank, world, local, pk, dist=None, cpu=True):
+        self.bof, self.ctx, self.rank, self.world, self.local, self.pk, self.dist = bof, ctx, rank, world, local, pk, dist
+        self.cpu = cpu and rank == 0 and world == 1
+        self.dev = f"cuda:{local}"
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def time_gpu(self, fn, iters=5, warm=3, flush=True):
+        """mean seconds per call (CUDA events), max over ranks"""
+        ts = []
+        for i in range(warm + iters):
+            if flush:
+                self.flush.zero_()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        return self.max_ranks(sum(ts) / len(ts))
+
+    def time_wall(self, fn, iters=2, warm=1):
+        """mean wall seconds per call of a blocking host entry point, bracketed by barriers, max over ranks"""
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        self.barrier()
+        return self.max_ranks(time.perf_counter() - t0) / iters
+
+
+def ncu_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/r02/traffic.json)"""
+    p = ROOT / "profiles" / "r02" / "traffic.json"
+    try:
+        return json.loads(p.read_text()).get(name)
+    except Exception:
+        return None
+
+
+def pinned(t, dtype=None):
+    h = torch.empty(t.shape, dtype=dtype or t.dtype, pin_memory=True)
+    h.copy_(t if dtype is None else t.to(dtype))
+    return h
+
+
+def gen_csr_gpu(m, n, nzr, seed, dev, row0=0, chunk=1 << 18):
+    """rows [row0, row0 + m) of the synthetic matrix: exactly nzr sorted columns per row, U[0,1) values.  The
+    generator is re-seeded per 2^18-row chunk, so a rank's shard is identical to the same rows of the full matrix."""
+    idx = torch.empty((m, nzr), dtype=torch.int32, device=dev)
+    vals = torch.empty((m, nzr), dtype=torch.float32, device=dev)
+    assert row0 % chunk == 0
+    for r0 in range(0, m, chunk):
+        r1 = min(m, r0 + chunk)
+        gen = torch.Generator(device=dev); gen.manual_seed(seed * 1000003 + (row0 + r0) // chunk)
+        c = torch.randint(0, n, (r1 - r0, nzr), device=dev, generator=gen, dtype=torch.int32)
+        idx[r0:r1] = torch.sort(c, dim=1).values
+        vals[r0:r1] = torch.rand((r1 - r0, nzr), device=dev, generator=gen)
+    offs = torch.arange(0, (m + 1) * nzr, nzr, dtype=torch.int64, device=dev)
+    return vals.reshape(-1), idx.reshape(-1), offs
+
+
+def shard_rows(m, world, rank, align=1 << 18):
+    """contiguous row shard, aligned to the generator chunk (equal nnz per row -> also nnz-balanced)"""
+    per = -(-m // world)
+    per = -(-per // align) * align
+    r0 = min(m, rank * per)
+    return r0, min(m, r0 + per)
+
+
+def spmm_bytes(nnz, m, n, k, beta=0.0):
+    gather = nnz * 8 + (m + 1) * 8 + nnz * k * 4 + m * k * 4 * (2 if beta else 1)
+    mn = nnz * 8 + (m + 1) * 8 + n * k * 4 + m * k * 4 * (2 if beta else 1)
+    return gather, mn
+
+
+def sampled_spmm_ref(rows, offs_h, idx_h, vals_h, B_h, r_base=0):
+    """fp64 reference of selected rows of C = A B from HOST arrays (idx int64 or int32)"""
+    out = np.zeros((len(rows), B_h.shape[1]), np.float64)
+    for i, r in enumerate(rows):
+        z0, z1 = int(offs_h[r]), int(offs_h[r + 1])
+        cols = idx_h[z0:z1].numpy().astype(np.int64)
+        out[i] = (vals_h[z0:z1].numpy().astype(np.float64)[:, None] * B_h[cols].numpy().astype(np.float64)).sum(0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ cfg-1
+def csrmm_cfg1(env: Env):
+    """configs[0]: in_mem_csrmm 262144^2, 64 nnz/row, k = 128 (the reference's own CPU-runnable case)"""
+    import oracle
+    from oracle import ref_run as rr
+
+    ctx, world, rank = env.ctx, env.world, env.rank
+    m = n = 262144
+    k, nzr = 128, 64
+    a, ia, ja = oracle.gen_csr(m, n, nzr, seed=0x5EED0001)
+    B = oracle.gen_dense((n, k), seed=0x5EED0011)
+    from bof_b200 import dist as bdist
+    r0, r1 = bdist.nnz_balanced_shard(ia, world, rank)
+    mr = r1 - r0
+    z0, z1 = int(ia[r0]), int(ia[r1])
+    nnz_r, nnz = z1 - z0, int(ia[m])
+    vals = torch.from_numpy(a[z0:z1]).to(env.dev)
+    idx = torch.from_numpy(ja[z0:z1].astype(np.int32)).to(env.dev)
+    offs = torch.from_numpy(ia[r0:r1 + 1] - ia[r0]).to(env.dev)
+    Bd = torch.from_numpy(B).to(env.dev)
+    Cd = torch.full((mr, k), float("nan"), device=env.dev)
+    t = env.time_gpu(lambda: ctx.spmm("R", mr, n, k, 1.0, vals, idx, offs, Bd, k, 0.0, Cd, k), flush=True)
+    g, mn = spmm_bytes(nnz_r, mr, n, k)
+    rec = {"workload": "csrmm 262144^2, 64 nnz/row, x dense 262144x128 fp32, alpha=1 beta=0 (BASELINE.json configs[0])",
+           "sharding": f"nnz-balanced row blocks over {world} rank(s), B replicated, no collective",
+           "metric": "csrmm_gflops", "value": 2.0 * nnz * k / t / 1e9, "unit": "GFLOP/s", "ms": t * 1e3,
+           "l2": "flushed (256 MiB memset) between iterations",
+           "roofline": {"bound": "hbm", "achieved": g / t / 1e9, "peak": env.pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": g / t / 1e9 / env.pk["hbm_gbs"], "model": "bytes_gather (SURVEY.md 8d, I=4), uncapped: L2 "
+                        "absorbs part of the gathers at this size", "achieved_bytes_min": mn / t / 1e9,
+                        "frac_bytes_min": mn / t / 1e9 / env.pk["hbm_gbs"], "traffic": ncu_traffic("spmm_cfg1"),
+                        "kernel": "spmm_csr_rm_vec_kernel"}}
+    C_dev = Cd.cpu().numpy()
+    # e2e through bof_host_csrmm, pinned host operands (this rank's row block)
+    a_h, ja_h = pinned(torch.from_numpy(a[z0:z1])), pinned(torch.from_numpy(ja[z0:z1]))
+    ia_h = pinned(torch.from_numpy(ia[r0:r1 + 1] - ia[r0]))
+    B_h, C_h = pinned(torch.from_numpy(B)), torch.empty((mr, k), dtype=torch.float32, pin_memory=True)
+    te = env.time_wall(lambda: ctx.host_csrmm("N", mr, n, k, 1.0, 0.0, a_h, ia_h, ja_h, "R", B_h, C_h), iters=3, warm=2)
+    st = ctx.stats()
+    rec["e2e"] = {"value": 2.0 * nnz * k / te / 1e9, "unit": "GFLOP/s", "ms": te * 1e3, "h2d_bytes_per_step": st.h2d_bytes,
+                  "d2h_bytes_per_step": st.d2h_bytes, "api": "bof_host_csrmm (C ABI behind flash::csrmm), pinned host buffers"}
+    # parity of the timed buffers: against the reference's own in_mem_csrmm driver when it is on this box
+    if env.rank == 0:
+        par = {}
+        ref32 = oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32))
+        par["rel_fro_vs_oracle_device"] = oracle.rel_fro(C_dev, ref32[r0:r1])
+        par["rel_fro_vs_oracle_e2e"] = oracle.rel_fro(C_h.numpy(), ref32[r0:r1])
+        if env.cpu and rr.available():
+            try:
+                c_ref, secs = rr.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32), want_time=True)
+                par["rel_fro_vs_reference_driver"] = oracle.rel_fro(C_dev, c_ref[r0:r1])
+                if secs:
+                    rec["cpu_baseline"] = {"value": 2.0 * nnz * k / secs / 1e9, "unit": "GFLOP/s", "cores": os.cpu_count(),
+                                           "kind": "reference", "sample": "the whole workload through oracle/_ref/in_mem_csrmm_driver "
+                                           f"(unmodified drivers/in_mem_csrmm.cpp -> mkl_scsrmm), its own timer: {secs:.3f} s"}
+            except Exception as ex:
+                par["reference_driver_error"] = repr(ex)[:200]
+        rec["parity"] = par
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------ cfg-3
+def csrmm_cfg3(env: Env, scale=1.0):
+    """configs[2]: flash::csrmm out-of-core, CSR 2^23 x 2^23, 100 nnz/row, x dense 2^23 x 256"""
+    ctx, world, rank = env.ctx, env.world, env.rank
+    m = n = int((1 << 23) * scale)
+    k, nzr = 256, 100
+    r0, r1 = shard_rows(m, world, rank)
+    mr = r1 - r0
+    vals, idx, offs = gen_csr_gpu(mr, n, nzr, 3, env.dev, row0=r0)
+    nnz_r, nnz = mr * nzr, m * nzr
+    genb = torch.Generator(device=env.dev); genb.manual_seed(0x5EED0031)
+    B = torch.rand((n, k), device=env.dev, generator=genb)
+    Cm = torch.full((mr, k), float("nan"), device=env.dev)
+    t = env.time_gpu(lambda: ctx.spmm("R", mr, n, k, 1.0, vals, idx, offs, B, k, 0.0, Cm, k), iters=3, flush=False)
+    g, mn = spmm_bytes(nnz_r, mr, n, k)
+    rec = {"workload": f"flash::csrmm CSR {m}x{n}, 100 nnz/row x dense {n}x256 fp32, alpha=1 beta=0 (BASELINE.json configs[2])",
+           "sharding": f"row blocks over {world} rank(s), B replicated, no collective on the data path",
+           "metric": "csrmm_gflops", "value": 2.0 * nnz * k / t / 1e9, "unit": "GFLOP/s", "ms": t * 1e3,
+           "l2": "B (8.6 GB) exceeds L2; no flush",
+           "roofline": {"bound": "hbm", "achieved": g / t / 1e9, "peak": env.pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": g / t / 1e9 / env.pk["hbm_gbs"], "model": "bytes_gather (SURVEY.md 8d, I=4)",
+                        "achieved_bytes_min": mn / t / 1e9, "traffic": ncu_traffic("spmm_cfg3"), "kernel": "spmm_csr_rm_vec_kernel"}}
+    # checksum of checksums on the timed buffer (size-independent property)
+    colsum = torch.zeros(n, device=env.dev, dtype=torch.float64).index_add_(0, idx.long(), vals.double())
+    chk = float((Cm.double().sum() - (colsum * B.double().sum(1)).sum()).abs() / Cm.double().sum().abs())
+    del colsum
+    # host copies (file format: int64 indices) for the end-to-end legs
+    a_h, ja_h, ia_h = pinned(vals), pinned(idx, torch.int64), pinned(offs)
+    B_h = pinned(B)
+    C_h = torch.empty((mr, k), dtype=torch.float32, pin_memory=True)
+    rows = np.random.default_rng(5).integers(0, mr, 256)
+    ref = sampled_spmm_ref(rows, ia_h, ja_h, a_h, B_h)
+    got_dev = Cm[torch.from_numpy(rows).to(env.dev)].cpu().numpy()
+    par = {"checksum_rel_err": chk, "rel_fro_sampled_rows_device": float(np.linalg.norm(got_dev - ref) / np.linalg.norm(ref)),
+           "sampled_rows": int(rows.size)}
+    del vals, idx, B, Cm
+    torch.cuda.empty_cache()
+    te = env.time_wall(lambda: ctx.host_csrmm("N", mr, n, k, 1.0, 0.0, a_h, ia_h, ja_h, "R", B_h, C_h), iters=2, warm=1)
+    st = ctx.stats()
+    streamed = (nnz * 12 + (m + 1) * 8) + n * k * 4 + m * k * 4
+    rec["e2e"] = {"value": 2.0 * nnz * k / te / 1e9, "unit": "GFLOP/s", "ms": te * 1e3, "h2d_bytes_per_step": st.h2d_bytes,
+                  "d2h_bytes_per_step": st.d2h_bytes, "streamed_gbs": streamed / te / 1e9, "h2d_gbs_per_gpu": st.h2d_bytes / te / 1e9,
+                  "api": "bof_host_csrmm, pinned host buffers, B uploaded by every rank (replicated)"}
+    par["rel_fro_sampled_rows_e2e"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
+    if world > 1:
+        # every rank uploads 1/N of B, NVLink all-gather, then the row-block pipeline on the device copy
+        from bof_b200 import dist as bdist
+        Bdev = torch.empty((n, k), device=env.dev)
+
+        def step():
+            up = bdist.allgather_dense(B_h, Bdev)
+            ctx.host_csrmm_devb(mr, n, k, 1.0, 0.0, a_h, ia_h, ja_h, Bdev, C_h)
+            return up
+        tg = env.time_wall(step, iters=2, warm=1)
+        st = ctx.stats()
+        rec["e2e_allgather"] = {"value": 2.0 * nnz * k / tg / 1e9, "unit": "GFLOP/s", "ms": tg * 1e3,
+                                "h2d_bytes_per_step": st.h2d_bytes + n * k * 4 // world, "d2h_bytes_per_step": st.d2h_bytes,
+                                "api": "B slice H2D + NCCL all-gather over NVLink, then bof_host_csrmm_devb"}
+        par["rel_fro_sampled_rows_allgather"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
+        del Bdev
+    if env.cpu:
+        try:
+            from oracle import mkl
+            ms = min(mr, 100001)   # one reference task: rows/block = min(MAX_NNZS / 100, CSRMM_RM_RBLK_SIZE)
+            h = mkl.Csr(ms, n, a_h[:ms * nzr].numpy(), ia_h[:ms + 1].numpy(), ja_h[:ms * nzr].numpy())
+            Bn = B_h.numpy()
+            out = np.zeros((ms, k), np.float32)
+            h.mm("N", k, 1.0, Bn, 0.0, out)
+            t0 = time.perf_counter(); h.mm("N", k, 1.0, Bn, 0.0, out); secs = time.perf_counter() - t0
+            h.close()
+            par["rel_fro_mkl_vs_gpu_first_rows"] = float(np.linalg.norm(out[:4096] - C_h[:4096].numpy()) / np.linalg.norm(out[:4096]))
+            rec["cpu_baseline"] = {"value": 2.0 * ms * nzr * k / secs / 1e9, "unit": "GFLOP/s", "cores": mkl.max_threads(), "kind": "port",
+                                   "sample": f"mkl_sparse_s_mm (oneMKL, the call behind mkl_scsrmm) on one reference csrmm task: the first {ms} rows "
+                                             f"x the full B, {secs:.2f} s"}
+        except Exception as ex:
+            rec["cpu_baseline"] = {"error": repr(ex)[:200]}
+    rec["parity"] = par
+    return rec, (a_h, ja_h, ia_h, m, n, nzr, r0, r1)
+
+
+# ------------------------------------------------------------------------------------------------ cfg-4
+def cfg4(env: Env, host_csr, scale=1.0):
+    """configs[3]: flash::csrgemv 'N' / 'T' and flash::csrcsc on the cfg-3 matrix"""
+    ctx, world, rank = env.ctx, env.world, env.rank
+    a_h, ja_h, ia_h, m, n, nzr, r0, r1 = host_csr
+    mr = r1 - r0
+    nnz_r, nnz = mr * nzr, m * nzr
+    vals = a_h.to(env.dev, non_blocking=True)
+    idx = torch.empty(nnz_r, dtype=torch.int32, device=env.dev)
+    for z0 in range(0, nnz_r, 1 << 26):
+        idx[z0:z0 + (1 << 26)] = ja_h[z0:z0 + (1 << 26)].to(env.dev).to(torch.int32)
+    offs = ia_h.to(env.dev)
+    genx = torch.Generator(device=env.dev); genx.manual_seed(0x5EED0041)
+    x = torch.rand(n, device=env.dev, generator=genx)
+    xt_full = torch.rand(m, device=env.dev, generator=genx)
+    out = {}
+    # ---- csrgemv
+    for trans in "NT":
+        xv = x if trans == "N" else xt_full[r0:r1].contiguous()
+        yv = torch.full((mr if trans == "N" else n,), float("nan"), device=env.dev)
+        t = env.time_gpu(lambda: ctx.spmv(trans, mr, n, vals, idx, offs, xv, yv), iters=5, flush=True)
+        byts = nnz_r * 8 + (mr + 1) * 8 + n * 4 + mr * 4
+        rec = {"workload": f"flash::csrgemv '{trans}' on the {m}x{n} CSR, 100 nnz/row (BASELINE.json configs[3])",
+               "sharding": ("row blocks per rank, x replicated, y disjoint, no collective" if trans == "N" else
+                            "row blocks per rank, full-length partial y per rank summed on the host in rank order"),
+               "metric": "csrgemv_gflops", "value": 2.0 * nnz / t / 1e9, "unit": "GFLOP/s", "ms": t * 1e3,
+               "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": env.pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": byts / t / 1e9 / env.pk["hbm_gbs"], "model": "nnz*(4+4) + offsets + x + y (SURVEY.md 8d, I=4)",
+                            "traffic": ncu_traffic(f"spmv_{trans.lower()}_cfg4"), "kernel": f"spmv_csr_{trans.lower()}"}}
+        # parity on the timed buffer, fp64 on the device in chunks
+        if trans == "N":
+            rows = torch.from_numpy(np.random.default_rng(6).integers(0, mr, 4096)).to(env.dev)
+            zz = (offs[rows][:, None] + torch.arange(nzr, device=env.dev)[None, :]).reshape(-1)
+            ref = (vals[zz].double() * x[idx[zz].long()].double()).reshape(-1, nzr).sum(1)
+            rec["parity"] = {"rel_fro_sampled_rows": float((yv[rows].double() - ref).norm() / ref.norm()), "sampled_rows": 4096}
+        else:
+            ref = torch.zeros(n, dtype=torch.float64, device=env.dev)
+            step = 1 << 20
+            for q0 in range(0, mr, step):
+                q1 = min(mr, q0 + step)
+                z0, z1 = q0 * nzr, q1 * nzr
+                w = (vals[z0:z1].double().reshape(-1, nzr) * xv[q0:q1].double()[:, None]).reshape(-1)
+                ref.index_add_(0, idx[z0:z1].long(), w)
+            rec["parity"] = {"rel_fro_full": float((yv.double() - ref).norm() / ref.norm())}
+            del ref
+        # e2e: host entry point, pinned
+        x_h = pinned(xv)
+        y_h = torch.empty(yv.shape, dtype=torch.float32, pin_memory=True)
+        te = env.time_wall(lambda: ctx.host_csrgemv(trans, mr, n, a_h, ia_h, ja_h, x_h, y_h), iters=2, warm=1)
+        st = ctx.stats()
+        rec["e2e"] = {"value": 2.0 * nnz / te / 1e9, "unit": "GFLOP/s", "ms": te * 1e3, "h2d_bytes_per_step": st.h2d_bytes,
+                      "d2h_bytes_per_step": st.d2h_bytes, "h2d_gbs_per_gpu": st.h2d_bytes / te / 1e9,
+                      "api": "bof_host_csrgemv, pinned host buffers" + ("" if trans == "N" or world == 1 else
+                                                                         " (+ host sum of the rank partials, not timed)")}
+        rec["parity"]["rel_fro_e2e_vs_device"] = float((y_h.to(env.dev).double() - yv.double()).norm() / yv.double().norm())
+        if env.cpu and trans == "N":
+            try:
+                from oracle import mkl
+                ms = min(mr, 1 << 20)
+                h = mkl.Csr(ms, n, a_h[:ms * nzr].numpy(), ia_h[:ms + 1].numpy(), ja_h[:ms * nzr].numpy())
+                xn, yo = x_h.numpy(), np.zeros(ms, np.float32)
+                h.mv("N", xn, yo)
+                t0 = time.perf_counter(); h.mv("N", xn, yo); secs = time.perf_counter() - t0
+                h.close()
+                rec["cpu_baseline"] = {"value": 2.0 * ms * nzr / secs / 1e9, "unit": "GFLOP/s", "cores": mkl.max_threads(), "kind": "port",
+                                       "sample": f"mkl_sparse_s_mv (oneMKL, the call behind mkl_cspblas_scsrgemv) on the first {ms} rows, {secs:.3f} s"}
+            except Exception as ex:
+                rec["cpu_baseline"] = {"error": repr(ex)[:200]}
+        out[f"csrgemv_{trans}_cfg4"] = rec
+        del yv
+    del x, xt_full
+    # ---- csrcsc: replicas only: every rank transposes its own copy of ITS row block
+    o1 = torch.empty(n + 1, dtype=torch.int64, device=env.dev)
+    i1 = torch.empty(nnz_r, dtype=torch.int32, device=env.dev)
+    v1 = torch.empty(nnz_r, device=env.dev)
+    ws = ctx.csr2csc_workspace(mr, n, nnz_r)
+    t = env.time_gpu(lambda: ctx.csr2csc(mr, n, nnz_r, offs, idx, vals, o1, i1, v1, ws=ws), iters=3, warm=3, flush=False)
+    ideal = nnz_r * 20 + (mr + n + 2) * 8
+    rec = {"workload": f"flash::csrcsc of the {m}x{n} CSR, 100 nnz/row (BASELINE.json configs[3])" +
+                       ("" if world == 1 else f"; replicas only: each of the {world} ranks transposes its {mr}-row block, no exchange"),
+           "metric": "csrcsc_gnnz_per_s", "value": env.sum_ranks(nnz_r) / t / 1e9, "unit": "Gnnz/s", "ms": t * 1e3,
+           "roofline": {"bound": "hbm", "achieved": ideal / t / 1e9, "peak": env.pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ideal / t / 1e9 / env.pk["hbm_gbs"], "model": "single-pass ideal 20 B/nnz (SURVEY.md 8d, I=4); the two "
+                        "radix passes move ~50 B/nnz", "traffic": ncu_traffic("csrcsc_cfg4"), "kernel": "radix_hist/scan/scatter x 2 passes"}}
+    ok_hist = bool(torch.equal(torch.bincount(idx.long(), minlength=n), o1[1:] - o1[:-1]))
+    o2 = torch.empty(mr + 1, dtype=torch.int64, device=env.dev); i2 = torch.empty_like(i1); v2 = torch.empty_like(v1)
+    ctx.csr2csc(n, mr, nnz_r, o1, i1, v1, o2, i2, v2, ws=ws)
+    same = bool(torch.equal(o2, offs) and torch.equal(i2, idx) and torch.equal(v2.view(torch.int32), vals.view(torch.int32)))
+    # exact check of the first 4096 columns against a stable sort of the entries that fall into them
+    sel = torch.nonzero(idx < 4096).reshape(-1)
+    order = torch.argsort(idx[sel].long(), stable=True)
+    hi = int(o1[4096])
+    exact = bool(torch.equal(i1[:hi].long(), (sel[order] // nzr)) and torch.equal(v1[:hi].view(torch.int32), vals[sel[order]].view(torch.int32)))
+    rec["parity"] = {"bit_exact_first_4096_columns_vs_stable_sort": exact, "double_transpose_bit_exact": same,
+                     "column_histogram_matches_offsets": ok_hist}
+    del ws, o2, i2, v2, sel, order
+    torch.cuda.empty_cache()
+    at_h = torch.empty(nnz_r, dtype=torch.float32, pin_memory=True); jat_h = torch.empty(nnz_r, dtype=torch.int64, pin_memory=True)
+    iat_h = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+    te = env.time_wall(lambda: ctx.host_csrcsc(mr, n, ia_h, ja_h, a_h, iat_h, jat_h, at_h), iters=1, warm=1)
+    st = ctx.stats()
+    rec["e2e"] = {"value": env.sum_ranks(nnz_r) / te / 1e9, "unit": "Gnnz/s", "ms": te * 1e3, "h2d_bytes_per_step": st.h2d_bytes,
+                  "d2h_bytes_per_step": st.d2h_bytes, "pcie_gbs_per_gpu": (st.h2d_bytes + st.d2h_bytes) / te / 1e9,
+                  "api": "bof_host_csrcsc, pinned host buffers (int64 indices both ways)"}
+    rec["parity"]["e2e_equals_device"] = bool(torch.equal(jat_h[:1 << 22].to(env.dev).to(torch.int32), i1[:1 << 22]) and
+                                              torch.equal(iat_h.to(env.dev), o1))
+    if env.cpu:
+        try:
+            import oracle
+            ms = min(mr, 1 << 20)
+            t0 = time.perf_counter()
+            oracle.csrcsc(ms, n, ia_h[:ms + 1].numpy(), ja_h[:ms * nzr].numpy(), a_h[:ms * nzr].numpy())
+            secs = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": ms * nzr / secs / 1e9, "unit": "Gnnz/s", "cores": 1, "kind": "port",
+                                   "sample": f"stable counting-sort restatement of mkl_scsrcsc (oracle.c, one thread) on the first {ms} rows, {secs:.2f} s"}
+        except Exception as ex:
+            rec["cpu_baseline"] = {"error": repr(ex)[:200]}
+    out["csrcsc_cfg4"] = rec
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ cfg-5
+def kmeans_cfg5(env: Env, scale=1.0, iters=20):
+    """configs[4]: kmeans 10M x 256 fp32 points, k = 1024, 20 iterations; NCCL allreduce of sums and counts at N > 1"""
+    import oracle
+    from bof_b200 import dist as bdist
+
+    bof, ctx, world, rank = env.bof, env.ctx, env.world, env.rank
+    P, K, d = int(10_000_000 * scale), 1024, 256
+    p0, p1 = bdist.row_shard(P, world, rank)
+    n_loc = p1 - p0
+    gen = torch.Generator(device=env.dev); gen.manual_seed(0x5EED0051)
+    cent_true = torch.randn((K, d), device=env.dev, generator=gen) * 4      # same on every rank
+    pts_h = torch.empty((n_loc, d), dtype=torch.float32, pin_memory=True)
+    genp = torch.Generator(device=env.dev); genp.manual_seed(0x5EED0052 + rank)
+    for q0 in range(0, n_loc, 1 << 20):
+        q1 = min(n_loc, q0 + (1 << 20))
+        lab = torch.randint(0, K, (q1 - q0,), device=env.dev, generator=genp)
+        pts_h[q0:q1].copy_(cent_true[lab] + 0.5 * torch.randn((q1 - q0, d), device=env.dev, generator=genp))
+    # ties-free start: one perturbed true centre per cluster
+    c0 = (cent_true + 0.25 * torch.randn((K, d), device=env.dev, generator=gen)).cpu()
+    torch.cuda.synchronize()
+
+    def run(n_iter):
+        km = bof.KMeans(ctx, n_loc, K, d, pts_h, c0)     # uploads the shard, norms, operand planes
+        bdist.lloyd(km, n_iter)
+        cent = np.zeros((K, d), np.float32)
+        km.get(cent, None)
+        return km, cent
+
+    km, _ = run(2)   # warm-up (allocations, NCCL channels, clocks)
+    km.close()
+    # device-resident: the 20 iterations only
+    km = bof.KMeans(ctx, n_loc, K, d, pts_h, c0)
+    bdist.lloyd(km, 3)
+    env.barrier()
+    stream = torch.cuda.ExternalStream(km.stream(), device=env.local)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(stream)
+    bdist.lloyd(km, iters)
+    e1.record(stream)
+    stream.synchronize()
+    t = env.max_ranks(e0.elapsed_time(e1) * 1e-3)
+    flops = 2.0 * P * K * d * iters
+    tf32 = env.pk.get("tf32_sustained")
+    bf16 = env.pk["bf16_sustained"]
+    peak_h = 1.0 / (1.0 / tf32 + 2.0 / bf16) if tf32 else None
+    rec = {"workload": f"kmeans {P}x{d} fp32 points, k={K}, {iters} Lloyd iterations (BASELINE.json configs[4])",
+           "sharding": f"points sharded over {world} rank(s) and resident; " + ("one NCCL all_reduce(SUM) of K*d+K fp32 per iteration "
+                       "on the library's stream" if world > 1 else "no collective at 1 GPU"),
+           "metric": "kmeans_distance_tflops", "value": flops / t / 1e12, "unit": "TFLOP/s", "ms_per_iter": t / iters * 1e3,
+           "roofline": {"bound": "tensor", "achieved": flops / t / 1e12 / world, "peak": peak_h, "unit": "TFLOP/s",
+                        "frac": (flops / t / 1e12 / world / peak_h) if peak_h else None, "model": "2*P*K*d useful flops per iteration over the WHOLE "
+                        "iteration (assign + reduce + update), per GPU, against 1/(1/TF32 + 2/BF16) (hybrid split)",
+                        "frac_3xtf32": (flops / t / 1e12 / world / (tf32 / 3.0)) if tf32 else None, "traffic": ncu_traffic("kmeans_assign_cfg5"),
+                        "kernel": "gemm3xtf32_kernel<2,EPI_ARGMIN>"}}
+    # parity on the resident state: centres after `iters + 3` iterations -> one more assignment of sampled points
+    cent = np.zeros((K, d), np.float32)
+    km.get(cent, None)
+    km.local_step()                                   # assignment against `cent`
+    assign = np.zeros(n_loc, np.int64)
+    km.get(None, assign)
+    sel = np.random.default_rng(7).integers(0, n_loc, 16384)
+    ps = pts_h[torch.from_numpy(sel)].numpy()
+    a_ref, margin = oracle.kmeans_assign(ps, cent)
+    clear = margin > 1e-3 * (1.0 + np.einsum("ij,ij->i", ps, ps))
+    par = {"assignments_sampled": int(sel.size), "ties_free_fraction": float(clear.mean()),
+           "assignment_mismatches_on_ties_free": int((assign[sel][clear] != a_ref[clear]).sum())}
+    if world == 1:
+        # centroid update of the GPU against the oracle's (reference order) on the GPU's own assignment
+        sub = slice(0, min(n_loc, 1 << 20))
+        ref_c, ref_n = oracle.kmeans_update(pts_h[sub].numpy(), assign[sub], K, mode=0)
+        pd = pts_h[sub].to(env.dev); ad = torch.from_numpy(assign[sub].astype(np.int32)).to(env.dev)
+        sums = torch.empty((K, d), device=env.dev); cnts = torch.empty(K, device=env.dev)
+        ctx.kmeans_reduce(pd.shape[0], K, d, pd, ad, sums, cnts)
+        got_c = (sums / cnts.clamp(min=1)[:, None]).cpu().numpy()
+        par["centroid_rel_fro_vs_oracle_first_1M_points"] = oracle.rel_fro(got_c, ref_c)
+        par["counts_equal"] = bool(np.array_equal(cnts.cpu().numpy().astype(np.int64), ref_n))
+    km.close()
+    rec["parity"] = par
+    # e2e: upload + norms + planes + 20 iterations + download of centres and assignments
+    cent_o = np.zeros((K, d), np.float32)
+    a_o = np.zeros(n_loc, np.int64)
+
+    def e2e():
+        km2 = bof.KMeans(ctx, n_loc, K, d, pts_h, c0)
+        bdist.lloyd(km2, iters)
+        km2.get(cent_o, a_o)
+        km2.close()
+    te = env.time_wall(e2e, iters=1, warm=0)
+    rec["e2e"] = {"value": flops / te / 1e12, "unit": "TFLOP/s", "ms": te * 1e3, "h2d_bytes_per_step": n_loc * d * 4 + K * d * 4,
+                  "d2h_bytes_per_step": K * d * 4 + n_loc * 4, "api": "bof_kmeans_open / local_step / update / get (flash::kmeans_lloyd), pinned host points"}
+    if env.cpu:
+        try:
+            from oracle import mkl
+            ns = 65536
+            ps = pts_h[:ns].numpy()
+            D = np.zeros((ns, K), np.float32)
+            ct = np.ascontiguousarray(cent.T)
+            mkl.sgemm_rowmajor(ns, K, d, -2.0, ps, ct, 0.0, D)
+            t0 = time.perf_counter()
+            mkl.sgemm_rowmajor(ns, K, d, -2.0, ps, ct, 0.0, D)
+            D += oracle.row_sqnorm(cent)[None, :]; D += oracle.row_sqnorm(ps)[:, None]
+            a_c = np.abs(D).argmin(1)
+            oracle.kmeans_update(ps, a_c.astype(np.int64), K, mode=0)
+            secs = time.perf_counter() - t0
+            rec["cpu_baseline"] = {"value": 2.0 * ns * K * d / secs / 1e12, "unit": "TFLOP/s", "cores": mkl.max_threads(), "kind": "port",
+                                   "sample": f"one Lloyd iteration on {ns} points the way drivers/in_mem_kmeans.cpp does it: MKL sgemm distance tile + "
+                                             f"rank-1 terms + isamin + saxpy update, {secs:.3f} s"}
+        except Exception as ex:
+            rec["cpu_baseline"] = {"error": repr(ex)[:200]}
+    return rec
+
+
+def pcie_bandwidth(env: Env):
+    """pinned cudaMemcpyAsync H2D / D2H / both at once, 1 GiB each, all ranks concurrently (the out-of-core roofline
+    denominators: per GPU and aggregate over the ranks of this run)"""
+    nel = 1 << 28
+    h_in = torch.empty(nel, dtype=torch.float32, pin_memory=True); h_out = torch.empty(nel, dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty(nel, dtype=torch.float32, device=env.dev); d_out = torch.rand(nel, device=env.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {}
+    for name in ("h2d", "d2h", "both"):
+        best = 1e9
+        for _ in range(3):
+            env.barrier()
+            t0 = time.perf_counter()
+            if name in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if name in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, env.max_ranks(time.perf_counter() - t0))
+        per = (2 if name == "both" else 1) * nel * 4 / best / 1e9
+        res[name + "_gbs_per_gpu"] = per
+        res[name + "_gbs_aggregate"] = per * env.world
+    res["note"] = f"{env.world} rank(s) copying concurrently, slowest rank; 1 GiB pinned transfers"
+    return res

@@ -1,0 +1,30 @@
+#!/bin/bash
+# r02 trip 4: 8-bit radix with fused row ids (tests + cfg-4 timing + per-launch), then the full bench.py line with
+# every config in `extra`, and the reference arm.
+set -u
+cd "$(dirname "$0")/../.."
+OUT=gpurun_out/r02_t04; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_csrcsc.py tests/test_gpu_kmeans.py tests/test_gpu_ref_parity.py tests/test_gpu_resident.py -m gpu -q -p no:cacheprovider -x 2>&1 | tail -30 > $OUT/tests.txt
+tail -3 $OUT/tests.txt
+timeout 600 python tools/bench_csrcsc.py --bits 8 > $OUT/csrcsc_bench.txt 2>&1
+cat $OUT/csrcsc_bench.txt
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k regex:"radix_|scan_|segment_" -c 40 --csv --log-file $OUT/csrcsc_launches.csv \
+  python tools/bench_csrcsc.py --bits 8 --iters 1 > $OUT/ncu_stdout.txt 2>&1
+python tools/launch_list.py $OUT/csrcsc_launches.csv --per-launch kernel > $OUT/csrcsc_per_launch.txt 2>&1
+head -16 $OUT/csrcsc_per_launch.txt
+( time timeout 1500 python bench.py ) > $OUT/bench.json 2> $OUT/bench.err
+tail -3 $OUT/bench.err
+python - <<'PY'
+import json
+for l in open("gpurun_out/r02_t04/bench.json"):
+    if l.startswith("{"):
+        d = json.loads(l)
+        print("value", d["value"], "e2e", d["e2e"]["value"], "roofline", d["roofline"]["frac"])
+        for k, v in d["extra"].items():
+            print(k, json.dumps({kk: v.get(kk) for kk in ("value", "unit", "ms", "ms_per_iter", "bench_seconds", "error", "trace")}))
+            for sub in ("roofline", "e2e", "parity", "cpu_baseline"):
+                if sub in v: print("   ", sub, json.dumps(v[sub])[:400])
+PY
+( time timeout 600 python bench.py --impl reference --steps 2 --warmup 1 ) > $OUT/bench_ref.json 2> $OUT/bench_ref.err
+cat $OUT/bench_ref.json | cut -c1-600; tail -3 $OUT/bench_ref.err
