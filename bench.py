@@ -491,8 +491,10 @@ def main():
 
     torch.cuda.empty_cache()
     extra = {}
+    l2 = ctx.launch_count()
     if not args.no_extra:
         extra = run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local)
+    launches_extra = ctx.launch_count() - l2
 
     if rank == 0:
         line = {
@@ -506,7 +508,8 @@ def main():
                        "l2": "operands (4 GiB each) exceed the 126 MB L2; no flush needed",
                        "spot_check_max_rel_err": spot},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches_dev + launches_e2e),
+            "gpu_launches": int(launches_dev + launches_e2e + launches_extra),
+            "gpu_launches_detail": {"gemm_device_leg": int(launches_dev), "gemm_e2e_leg": int(launches_e2e), "extra": int(launches_extra)},
             "host": {"cpus": cpus_before, "numa_bound_cpus": numa_cpus}, "extra": extra,
         }
         print(json.dumps(line), flush=True)
