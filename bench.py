@@ -322,8 +322,8 @@ def run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local):
     if "pcie" in extra and "h2d_gbs_per_gpu" in extra["pcie"]:
         # out-of-core legs as multiples of the measured PCIe bound of THIS run (north_star: within 1.3x)
         h2d = extra["pcie"]["h2d_gbs_per_gpu"]
-        for key in ("csrmm_cfg3", "csrgemv_N_cfg4"):
-            e = extra.get(key, {}).get("e2e")
+        for key, sub in (("csrmm_cfg3", "e2e"), ("csrmm_cfg3", "e2e_shared_b"), ("csrgemv_N_cfg4", "e2e")):
+            e = extra.get(key, {}).get(sub)
             if e and e.get("h2d_bytes_per_step"):
                 bound_ms = e["h2d_bytes_per_step"] / h2d / 1e6
                 e["pcie_h2d_bound_ms"] = bound_ms
@@ -454,7 +454,8 @@ def main():
     torch.cuda.synchronize()
     e2e_steps = max(1, min(args.steps, 3))
     from bof_b200 import dist as bdist
-    Bdev = torch.empty((Kg, Ng), device="cuda") if world > 1 else None
+    if world > 1:
+        bdist.init_comm(ctx)   # the library's own communicator rank: panel broadcasts of B on its collective stream
 
     def e2e_step():
         """One flash::gemm on this rank's row shard, host buffers in, host buffer out."""
@@ -462,12 +463,12 @@ def main():
             ctx.host_gemm("R", "N", "N", Mr, Ng, Kg, 1.0, 0.0, Ah, Bh, Ch)  # returns after the D2H completed
             st_ = ctx.stats()
             return st_.h2d_bytes, st_.d2h_bytes
-        # N > 1: B is replicated.  Every rank uploads 1/N of it and the ranks all-gather over NVLink, so only
-        # the A shard, a B slice and the C shard cross this GPU's PCIe link.
-        up = bdist.allgather_dense(Bh, Bdev)
-        ctx.host_gemm_devb("N", "N", Mr, Ng, Kg, 1.0, 0.0, Ah, Bdev, Ch)
+        # N > 1: B is replicated.  bof_dist_gemm: panel j of B is uploaded by rank j % N only and broadcast over
+        # NVLink on the library's collective stream while the tensor cores work on the panels that have arrived;
+        # only the A shard, 1/N of B and the C shard cross this GPU's PCIe link.
+        ctx.dist_gemm("N", "N", Mr, Ng, Kg, 1.0, 0.0, Ah, Bh, Ch)
         st_ = ctx.stats()
-        return st_.h2d_bytes + up, st_.d2h_bytes
+        return st_.h2d_bytes, st_.d2h_bytes
 
     for _ in range(2):
         e2e_step()
@@ -483,11 +484,12 @@ def main():
            "d2h_bytes_per_step": d2h_b, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
            "pcie_gbs": (h2d_b + d2h_b) / t_e2e / 1e9,
            "api": "bof_host_gemm (C ABI behind flash::gemm), pinned host A/B/C" if world == 1 else
-                  "per rank: B slice H2D + NCCL all-gather over NVLink, then bof_host_gemm_devb; pinned host A/B/C"}
+                  "bof_dist_gemm (C ABI): per rank 1/N of B's column panels H2D + NCCL panel broadcasts over NVLink overlapped with "
+                  "the MMAs, C downloaded slab by slab; pinned host A/B/C"}
     i0 = int(torch.randint(0, Mr, (1,))); j0 = int(torch.randint(0, Ng, (1,)))
     ref0 = float((Ah[i0].double() * Bh[:, j0].double()).sum())
     e2e["spot_rel_err"] = abs(float(Ch[i0, j0]) - ref0) / abs(ref0)
-    del Ah, Bh, Ch, Bdev
+    del Ah, Bh, Ch
 
     torch.cuda.empty_cache()
     extra = {}

@@ -15,7 +15,7 @@ import ctypes as C
 from . import _capi
 from ._capi import BofConfig, BofError, BofStats, ch, load, ptr
 
-__all__ = ["Context", "KMeans", "ResidentCsr", "BofError", "BofStats", "load"]
+__all__ = ["Context", "KMeans", "ResidentCsr", "MultiGpu", "BofError", "BofStats", "load"]
 
 
 def _cur_stream() -> int:
@@ -159,6 +159,22 @@ class Context:
         self._check(self.lib.bof_host_kmeans_dist(self.h, ch(ord_), ch(ta), ch(tb), m, n, k, alpha, beta, ptr(a), ptr(b),
                                                   ptr(c), lda, ldb, ldc, ptr(c_l2sq), ptr(p_l2sq)))
 
+    # ---- multi-GPU: one communicator rank per context (bof_comm_*, bof_dist_*) ----
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.bof_comm_init(self.h, world, rank, C.cast(buf, C.c_void_p)))
+
+    def comm_world(self) -> int:
+        return int(self.lib.bof_comm_world(self.h))
+
+    def dist_gemm(self, ta, tb, m_local, n, k, alpha, beta, a_local, b, c_local, lda=0, ldb=0, ldc=0):
+        self._check(self.lib.bof_dist_gemm(self.h, ch(ta), ch(tb), m_local, n, k, alpha, beta, ptr(a_local), ptr(b),
+                                           ptr(c_local), lda, ldb, ldc))
+
+    def dist_csrmm(self, m_local, n, k, alpha, beta, a, ia, ja, b, c_local):
+        self._check(self.lib.bof_dist_csrmm(self.h, m_local, n, k, alpha, beta, ptr(a), ptr(ia), ptr(ja), ptr(b),
+                                            ptr(c_local)))
+
     def host_csrcsc(self, m, n, ia, ja, a, ia_tr, ja_tr, a_tr):
         self._check(self.lib.bof_host_csrcsc(self.h, m, n, ptr(ia), ptr(ja), ptr(a), ptr(ia_tr), ptr(ja_tr),
                                              ptr(a_tr)))
@@ -183,6 +199,14 @@ class KMeans:
 
     def update(self):
         self.ctx._check(self.ctx.lib.bof_kmeans_update(self.h))
+
+    def allreduce(self):
+        """NCCL sum of the partial buffer over the ranks of the context's communicator (no-op at world 1)"""
+        self.ctx._check(self.ctx.lib.bof_kmeans_allreduce(self.h))
+
+    def lloyd(self, iters: int):
+        """iters x (local_step, allreduce, update) inside the library; asynchronous until get()"""
+        self.ctx._check(self.ctx.lib.bof_kmeans_lloyd(self.h, iters))
 
     def get(self, centers_host=None, assign_host=None):
         self.ctx._check(self.ctx.lib.bof_kmeans_get(self.h, ptr(centers_host), ptr(assign_host)))
@@ -225,3 +249,63 @@ class ResidentCsr:
         if getattr(self, "h", None):
             self.ctx.lib.bof_csr_close(self.h)
             self.h = None
+
+
+def comm_unique_id() -> bytes:
+    """128-byte id for bof_comm_init; create on one rank and distribute (dist.init_comm does it over torch.distributed)."""
+    lib = load()
+    buf = C.create_string_buffer(128)
+    rc = lib.bof_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise BofError(rc, "bof_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+class MultiGpu:
+    """One process, several GPUs (bof_mgpu_*): what the C++ flash:: adapters use when BOF_GPUS > 1."""
+
+    def __init__(self, ndev: int = 0, devices=None, **cfg):
+        self.lib = load()
+        conf = BofConfig()
+        for k, v in cfg.items():
+            setattr(conf, k, v)
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        h = C.c_void_p()
+        rc = self.lib.bof_mgpu_create(C.byref(conf), len(devices) if devices else ndev, C.cast(devs, C.c_void_p) if devs else None,
+                                      C.byref(h))
+        if rc != 0:
+            raise BofError(rc, (self.lib.bof_last_error(None) or b"").decode())
+        self.h = h
+
+    def count(self) -> int:
+        return int(self.lib.bof_mgpu_count(self.h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BofError(rc, (self.lib.bof_mgpu_last_error(self.h) or b"").decode())
+
+    def gemm(self, ord_, ta, tb, m, n, k, alpha, beta, a, b, c, lda=0, ldb=0, ldc=0):
+        self._check(self.lib.bof_mgpu_gemm(self.h, ch(ord_), ch(ta), ch(tb), m, n, k, alpha, beta, ptr(a), ptr(b), ptr(c),
+                                           lda, ldb, ldc))
+
+    def csrmm(self, trans_a, m, n, k, alpha, beta, a, ia, ja, ord_b, b, c):
+        self._check(self.lib.bof_mgpu_csrmm(self.h, ch(trans_a), m, n, k, alpha, beta, ptr(a), ptr(ia), ptr(ja), ch(ord_b),
+                                            ptr(b), ptr(c)))
+
+    def csrgemv(self, trans_a, m, n, a, ia, ja, x, y):
+        self._check(self.lib.bof_mgpu_csrgemv(self.h, ch(trans_a), m, n, ptr(a), ptr(ia), ptr(ja), ptr(x), ptr(y)))
+
+    def kmeans_lloyd(self, npoints, ncenters, dim, points, centers, iters, assign=None):
+        self._check(self.lib.bof_mgpu_kmeans_lloyd(self.h, npoints, ncenters, dim, ptr(points), ptr(centers), iters,
+                                                   ptr(assign)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bof_mgpu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -96,7 +96,25 @@ PROTOTYPES = {
     "bof_kmeans_local_step": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "bof_kmeans_update": (C.c_int, [_vp]),
     "bof_kmeans_get": (C.c_int, [_vp, _vp, _vp]),
+    "bof_kmeans_allreduce": (C.c_int, [_vp]),
+    "bof_kmeans_lloyd": (C.c_int, [_vp, _i64]),
     "bof_kmeans_stream": (_vp, [_vp]),
+    "bof_comm_unique_id": (C.c_int, [_vp]),
+    "bof_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "bof_comm_finalize": (C.c_int, [_vp]),
+    "bof_comm_world": (C.c_int, [_vp]),
+    "bof_comm_rank": (C.c_int, [_vp]),
+    "bof_dist_gemm": (C.c_int, [_vp, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "bof_dist_csrmm": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "bof_mgpu_create": (C.c_int, [C.POINTER(BofConfig), C.c_int, _vp, C.POINTER(_vp)]),
+    "bof_mgpu_destroy": (C.c_int, [_vp]),
+    "bof_mgpu_count": (C.c_int, [_vp]),
+    "bof_mgpu_ctx": (_vp, [_vp, C.c_int]),
+    "bof_mgpu_last_error": (C.c_char_p, [_vp]),
+    "bof_mgpu_gemm": (C.c_int, [_vp, _ch, _ch, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _i64, _i64, _i64]),
+    "bof_mgpu_csrmm": (C.c_int, [_vp, _ch, _i64, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _ch, _vp, _vp]),
+    "bof_mgpu_csrgemv": (C.c_int, [_vp, _ch, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "bof_mgpu_kmeans_lloyd": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
     "bof_kmeans_close": (C.c_int, [_vp]),
 }
 

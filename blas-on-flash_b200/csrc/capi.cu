@@ -75,6 +75,7 @@ int bof_ctx_destroy(bof_ctx* ctx) {
   for (auto ev : ctx->events) cudaEventDestroy(ev);
   for (auto& m : ctx->trace) cudaEventDestroy(m.ev);
   for (auto ev : ctx->trace_pool) cudaEventDestroy(ev);
+  comm_destroy(ctx);
   staging_destroy(ctx);  // copy pools, drainer thread (joined first), pinned rings
   if (ctx->sync_ctr) cudaFree(ctx->sync_ctr);
   if (ctx->tk0) cudaEventDestroy(ctx->tk0);

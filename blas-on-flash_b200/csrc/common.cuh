@@ -36,6 +36,8 @@ class Drainer;   // background thread that copies landed device->host chunks out
 
 // The opaque context of the C ABI: one per process/GPU (replaces the static flash::sched,
 // src/lib_funcs.cpp:9 of the reference).
+namespace bof { struct CommState; }
+
 struct bof_ctx {
   bof_config cfg{};
   int device = 0;
@@ -72,6 +74,9 @@ struct bof_ctx {
   bool tk_valid = false;
   uint32_t* sync_ctr = nullptr;   // wave lock-step counters of the GEMM kernel
   size_t sync_ctr_count = 0;
+  // multi-GPU: communicator of this context's rank (comm.cu), collectives run on `coll`
+  bof::CommState* comm = nullptr;
+  cudaStream_t coll = nullptr;
 };
 
 namespace bof {
@@ -193,9 +198,12 @@ int launch_row_sqnorm(bof_ctx* ctx, cudaStream_t s, int64_t rows, int64_t dim, c
 size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t dim);
 int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
                             int64_t dim, const float* points, const int32_t* assign, float* sums,
-                            float* counts, void* ws, size_t ws_bytes);
+                            float* counts, void* ws, size_t ws_bytes, float* counts_hi = nullptr);
+// counts_hi != nullptr: the cluster sizes are split as counts = size & 4095, counts_hi = size >> 12 (both exact in fp32,
+// also after a sum over ranks); otherwise `counts` holds the size itself (exact below 2^24)
 int launch_kmeans_finalize(bof_ctx* ctx, cudaStream_t s, int64_t ncenters, int64_t dim,
-                           const float* sums, const float* counts, float* centers, float* c_l2sq);
+                           const float* sums, const float* counts, float* centers, float* c_l2sq,
+                           const float* counts_hi = nullptr);
 
 size_t csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz);
 int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t nnz,

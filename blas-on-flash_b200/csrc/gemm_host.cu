@@ -93,7 +93,8 @@ extern "C" {
 // on the device, so each C block crosses PCIe once.
 static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
                           float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc,
-                          bool q_on_device, const float* term_m = nullptr, const float* term_n = nullptr) {
+                          bool q_on_device, const float* term_m = nullptr, const float* term_n = nullptr,
+                          bool dist_q = false) {
   if (!ctx) return BOF_EINVAL;
   Canon cn;
   BOF_TRY(canon_gemm(ctx, ord, ta, tb, m, n, k, a, lda, b, ldb, ldc, &cn));
@@ -259,15 +260,36 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // When Q is K-major in the source its rows upload as contiguous panels: panel 0, then P block 0, then the
   // remaining panels; block 0 is computed panel by panel as they land, so only one panel and one P block of
   // PCIe time are exposed before the tensor cores start.
-  const bool q_panels = tensor && !q_on_device && (size_t)cn.No * K * 4 >= (256u << 20);
-  static const int64_t n_q_panels = getenv("BOF_GEMM_QPANELS") ? std::min(8, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 8;
+  // dist_q (bof_dist_gemm): Q is replicated over the ranks of the communicator.  Panel j is uploaded by rank
+  // j % world only and broadcast over NVLink on the collective stream, so Q crosses PCIe once per node; every
+  // rank consumes the panels in the same order as they arrive, exactly like its own uploads.
+  const int world = dist_q ? comm_world(ctx) : 1, rank = comm_rank(ctx);
+  const bool dist = dist_q && world > 1 && tensor;
+  const bool q_panels = tensor && !q_on_device && (dist || (size_t)cn.No * K * 4 >= (256u << 20));
+  static const int64_t n_q_panels_env = getenv("BOF_GEMM_QPANELS") ? std::min(16, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 0;
+  const int64_t n_q_panels = n_q_panels_env ? n_q_panels_env : (dist ? (world >= 8 ? 16 : 8) : 8);
   const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, n_q_panels), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
+  constexpr int EV_OWN = 64, EV_SLAB = 88;
   // Every panel is kept as its own tight block at qraw + n0*K: [rows x K] when Q is K-major in the source,
   // [K x rows] (a column range of the stored matrix, pitched copy) when it is not.
   std::vector<int64_t> pan_sr((size_t)n_qpan, 1), pan_sk((size_t)n_qpan, 1);
   auto upload_q_panel = [&](int j) -> int {
     const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
+    if (dist) {
+      const int owner = j % world;
+      if (cn.q_sk == 1) { pan_sr[j] = K; pan_sk[j] = 1; } else { pan_sr[j] = 1; pan_sk[j] = n1 - n0; }  // what upload_rows produces
+      if (owner == rank) {
+        BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &pan_sr[j], &pan_sk[j], ctx->h2d));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_OWN + j), ctx->h2d));
+        BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->coll, get_event(ctx, EV_OWN + j), 0));
+        trace_mark(ctx, ctx->h2d, "h2d: own Q panel landed", j);
+      }
+      BOF_TRY(comm_broadcast_f32(ctx, qraw + n0 * K, (size_t)(n1 - n0) * K, owner));
+      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->coll));
+      trace_mark(ctx, ctx->coll, "coll: Q panel broadcast done", j);
+      return BOF_OK;
+    }
     if (q_on_device) { pan_sr[j] = cn.q_sr; pan_sk[j] = cn.q_sk; }  // single panel, source strides
     else BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &pan_sr[j], &pan_sk[j], ctx->h2d));
     if (n_qpan == 1) { q_sr = pan_sr[0]; q_sk = pan_sk[0]; }
@@ -293,6 +315,17 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   const int npro = n_qpan > 1 ? std::min({nblk, NB - 1, n_qpan}) : 1;  // blocks handled by the prologue
   auto pan = [&](int j, int64_t* n0, int64_t* n1) { *n0 = (int64_t)j * qpan_rows; *n1 = std::min(cn.No, *n0 + qpan_rows); };
   const bool merge = tensor;  // the CUDA-core path multiplies one block per launch
+  // When every block rides in the prologue (a rank's shard of a multi-GPU job, or a small M), each (block, panel)
+  // product completes a column slab of C for good: download slab by slab behind the compute instead of whole blocks
+  // at the end, so only the last slab's download is exposed.
+  const bool slab_download = tensor && !with_terms && n_qpan > 1 && nblk <= npro;
+  uint64_t slab_ticket = 0;
+  auto fetch_slab = [&](int i, int64_t n0, int64_t n1, cudaEvent_t after) -> int {
+    const int g = i % NB;
+    const int64_t r0 = (int64_t)i * rb;
+    return d2h_transfer(ctx, c + r0 * cn.ldc + n0, (size_t)cn.ldc * 4, cblk_of(g) + n0, (size_t)cn.No * 4, (size_t)(n1 - n0) * 4,
+                        (size_t)rows_of(i), ctx->d2h, after, nullptr, &slab_ticket);
+  };
   // Uploads and launches are issued panel by panel: with pinned memory the order of issue is immaterial (everything
   // is asynchronous), but a pageable upload blocks this thread while it is staged, and launching only after the
   // whole prologue had been uploaded left the GPU idle for the first 170 ms at 32768^3 (BOF_TRACE).
@@ -313,8 +346,20 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
       BOF_TRY(prepare_block(t));
       BOF_TRY(gemm_blocks(t, 1, 0, n1));
     }
-    if (t == n_qpan - 1)
+    if (slab_download) {
+      cudaEvent_t ev = get_event(ctx, EV_SLAB + t);
+      BOF_CUDA(ctx, cudaEventRecord(ev, ctx->compute));
+      for (int i = 0; i < older; ++i) BOF_TRY(fetch_slab(i, n0, n1, ev));      // panel t of the earlier blocks
+      if (t < npro) BOF_TRY(fetch_slab(t, 0, n1, ev));                          // panels 0..t of block t
+    } else if (t == n_qpan - 1) {
       for (int i = 0; i < npro; ++i) BOF_TRY(finish_block(i));
+    }
+  }
+  if (slab_download) {
+    BOF_TRY(sync_all(ctx));
+    trace_dump(ctx, "bof_host_gemm");
+    stats_end(ctx);
+    return call_guard.done();
   }
   // ---- steady state: Q complete; keep NB blocks in flight, fetch the oldest before reusing its buffers ----
   int next_fetch = 0;
@@ -374,6 +419,12 @@ int bof_host_kmeans_dist(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, in
 int bof_host_gemm_devb(bof_ctx* ctx, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha, float beta,
                        const float* a, const float* b_dev, float* c, int64_t lda, int64_t ldb, int64_t ldc) {
   return host_gemm_impl(ctx, 'R', ta, tb, m, n, k, alpha, beta, a, b_dev, c, lda, ldb, ldc, true);
+}
+
+int bof_dist_gemm(bof_ctx* ctx, char ta, char tb, int64_t m_local, int64_t n, int64_t k, float alpha, float beta,
+                  const float* a_local, const float* b, float* c_local, int64_t lda, int64_t ldb, int64_t ldc) {
+  return host_gemm_impl(ctx, 'R', ta, tb, m_local, n, k, alpha, beta, a_local, b, c_local, lda, ldb, ldc, false, nullptr,
+                        nullptr, true);
 }
 
 }  // extern "C"

@@ -16,7 +16,7 @@ struct bof_kmeans {
   float* p_l2sq;        // P
   float* centers;       // K x dim
   float* c_l2sq;        // K
-  float* partial;       // [K*dim sums | K counts]
+  float* partial;       // [K*dim sums | K counts & 4095 | K counts >> 12]: the allreduce payload, every entry exact in fp32
   int32_t* assign;      // P
   void* ws_assign; size_t ws_assign_bytes;
   void* ws_reduce; size_t ws_reduce_bytes;
@@ -45,7 +45,7 @@ int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim
   struct Req { void** p; size_t bytes; } reqs[] = {
       {(void**)&km->points, P * dim * 4}, {&km->point_planes, bof_kmeans_point_planes_bytes(npoints, dim)},
       {(void**)&km->p_l2sq, P * 4}, {(void**)&km->centers, (size_t)ncenters * dim * 4},
-      {(void**)&km->c_l2sq, (size_t)ncenters * 4}, {(void**)&km->partial, ((size_t)ncenters * dim + ncenters) * 4},
+      {(void**)&km->c_l2sq, (size_t)ncenters * 4}, {(void**)&km->partial, ((size_t)ncenters * dim + 2 * ncenters) * 4},
       {(void**)&km->assign, P * 4}, {&km->ws_assign, km->ws_assign_bytes}, {&km->ws_reduce, km->ws_reduce_bytes},
       {(void**)&km->assign64, P * 8}};
   for (auto& r : reqs) {
@@ -73,17 +73,40 @@ int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_fl
   cudaStream_t s = ctx->compute;
   BOF_TRY(bof_kmeans_assign(ctx, s, km->npoints, km->ncenters, km->dim, km->points, km->centers, km->c_l2sq,
                             km->p_l2sq, km->assign, km->point_planes, km->ws_assign, km->ws_assign_bytes));
+  float* cnt_lo = km->partial + km->ncenters * km->dim;
   BOF_TRY(launch_kmeans_reduce_ws(ctx, s, km->npoints, km->ncenters, km->dim, km->points, km->assign, km->partial,
-                                  km->partial + km->ncenters * km->dim, km->ws_reduce, km->ws_reduce_bytes));
+                                  cnt_lo, km->ws_reduce, km->ws_reduce_bytes, cnt_lo + km->ncenters));
   if (dev_partial) *dev_partial = km->partial;
-  if (partial_floats) *partial_floats = (size_t)km->ncenters * km->dim + km->ncenters;
+  if (partial_floats) *partial_floats = (size_t)km->ncenters * km->dim + 2 * (size_t)km->ncenters;
   return BOF_OK;
 }
 
 int bof_kmeans_update(bof_kmeans* km) {
   if (!km) return BOF_EINVAL;
-  return launch_kmeans_finalize(km->ctx, km->ctx->compute, km->ncenters, km->dim, km->partial,
-                                km->partial + km->ncenters * km->dim, km->centers, km->c_l2sq);
+  float* cnt_lo = km->partial + km->ncenters * km->dim;
+  return launch_kmeans_finalize(km->ctx, km->ctx->compute, km->ncenters, km->dim, km->partial, cnt_lo, km->centers,
+                                km->c_l2sq, cnt_lo + km->ncenters);
+}
+
+// The one exchange step of the path: in-place NCCL sum of [sums | counts] over the ranks of this
+// context's communicator, on the stream the k-means kernels run on.  No-op without a communicator / at world 1.
+int bof_kmeans_allreduce(bof_kmeans* km) {
+  if (!km) return BOF_EINVAL;
+  if (comm_world(km->ctx) <= 1) return BOF_OK;
+  return comm_allreduce_sum_f32(km->ctx, km->partial, (size_t)km->ncenters * km->dim + 2 * (size_t)km->ncenters,
+                                km->ctx->compute);
+}
+
+// `iters` Lloyd iterations on the resident shard: assign + local sums, allreduce over the ranks, centroid update
+// (drivers/in_mem_kmeans.cpp:89-152 per iteration).  Asynchronous: bof_kmeans_get synchronises.
+int bof_kmeans_lloyd(bof_kmeans* km, int64_t iters) {
+  if (!km) return BOF_EINVAL;
+  for (int64_t it = 0; it < iters; ++it) {
+    BOF_TRY(bof_kmeans_local_step(km, nullptr, nullptr));
+    BOF_TRY(bof_kmeans_allreduce(km));
+    BOF_TRY(bof_kmeans_update(km));
+  }
+  return BOF_OK;
 }
 
 int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host) {

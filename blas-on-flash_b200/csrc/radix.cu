@@ -548,7 +548,8 @@ kmeans_partial_kernel(int64_t ncenters, int64_t dim, const float* __restrict__ p
 
 __global__ void __launch_bounds__(256)
 kmeans_combine_kernel(int64_t dim, const float* __restrict__ partial, const int64_t* __restrict__ seg_offs,
-                      const int32_t* __restrict__ seg_base, float* __restrict__ sums, float* __restrict__ counts) {
+                      const int32_t* __restrict__ seg_base, float* __restrict__ sums, float* __restrict__ counts,
+                      float* __restrict__ counts_hi) {
   const int64_t c = blockIdx.x;
   const int32_t s0 = seg_base[c], s1 = seg_base[c + 1];
   for (int64_t j = threadIdx.x; j < dim; j += blockDim.x) {
@@ -556,15 +557,26 @@ kmeans_combine_kernel(int64_t dim, const float* __restrict__ partial, const int6
     for (int32_t sgm = s0; sgm < s1; ++sgm) acc += partial[(int64_t)sgm * dim + j];
     sums[c * dim + j] = acc;
   }
-  if (threadIdx.x == 0) counts[c] = (float)(seg_offs[c + 1] - seg_offs[c]);
+  if (threadIdx.x == 0) {
+    // counts travel through an fp32 sum over the ranks: split into 12 low bits and the rest so that both parts stay
+    // exactly representable (a single float is exact only below 2^24 points per cluster)
+    const int64_t cnt = seg_offs[c + 1] - seg_offs[c];
+    if (counts_hi != nullptr) {
+      counts[c] = (float)(cnt & 4095);
+      counts_hi[c] = (float)(cnt >> 12);
+    } else {
+      counts[c] = (float)cnt;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
 kmeans_finalize_kernel(int64_t dim, const float* __restrict__ sums, const float* __restrict__ counts,
-                       float* __restrict__ centers, float* __restrict__ c_l2sq) {
+                       const float* __restrict__ counts_hi, float* __restrict__ centers, float* __restrict__ c_l2sq) {
   __shared__ float red[8];
   const int64_t c = blockIdx.x;
-  const float cnt = counts[c];
+  // with the split form both parts are exact integers (sums over the ranks included); recombine in fp64
+  const float cnt = counts_hi ? (float)((double)counts_hi[c] * 4096.0 + (double)counts[c]) : counts[c];
   const float inv = cnt > 0.f ? 1.f / cnt : 0.f;
   float acc = 0.f;
   for (int64_t j = threadIdx.x; j < dim; j += blockDim.x) {
@@ -661,7 +673,7 @@ size_t kmeans_reduce_workspace_bytes(int64_t npoints, int64_t ncenters, int64_t 
 
 int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64_t ncenters,
                             int64_t dim, const float* points, const int32_t* assign, float* sums,
-                            float* counts_out, void* ws, size_t ws_bytes) {
+                            float* counts_out, void* ws, size_t ws_bytes, float* counts_hi_out) {
   BOF_REQUIRE(ctx, npoints < (1ll << 31) && ncenters < (1ll << 31), "kmeans_reduce: extents must be below 2^31");
   BOF_REQUIRE(ctx, ncenters > 0 && dim > 0, "kmeans_reduce: empty problem");
   BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= kmeans_reduce_workspace_bytes(npoints, ncenters, dim),
@@ -701,15 +713,16 @@ int launch_kmeans_reduce_ws(bof_ctx* ctx, cudaStream_t s, int64_t npoints, int64
   kmeans_partial_kernel<<<(unsigned)km_max_segments(npoints, ncenters), 256, 0, s>>>(ncenters, dim, points, pin, seg,
                                                                                      seg_base, partial);
   BOF_LAUNCH_CHECK(ctx, "kmeans_partial_kernel");
-  kmeans_combine_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, partial, seg, seg_base, sums, counts_out);
+  kmeans_combine_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, partial, seg, seg_base, sums, counts_out, counts_hi_out);
   BOF_LAUNCH_CHECK(ctx, "kmeans_combine_kernel");
   return BOF_OK;
 }
 
 int launch_kmeans_finalize(bof_ctx* ctx, cudaStream_t s, int64_t ncenters, int64_t dim,
-                           const float* sums, const float* counts, float* centers, float* c_l2sq) {
+                           const float* sums, const float* counts, float* centers, float* c_l2sq,
+                           const float* counts_hi) {
   if (ncenters == 0) return BOF_OK;
-  kmeans_finalize_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, sums, counts, centers, c_l2sq);
+  kmeans_finalize_kernel<<<(unsigned)ncenters, 256, 0, s>>>(dim, sums, counts, counts_hi, centers, c_l2sq);
   BOF_LAUNCH_CHECK(ctx, "kmeans_finalize_kernel");
   return BOF_OK;
 }

@@ -29,7 +29,7 @@ extern "C" {
 
 static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
                            const float* a, const int64_t* ia, const int64_t* ja, char ord_b, const float* b, float* c,
-                           const float* b_dev) {
+                           const float* b_dev, bool dist_b = false) {
   if (!ctx) return BOF_EINVAL;
   BOF_REQUIRE(ctx, is_nt(trans_a), "csrmm: unrecognized value for param trans_a = '%c'", trans_a);
   BOF_REQUIRE(ctx, b_dev == nullptr || (trans_a == 'N' && ord_b == 'R'),
@@ -53,8 +53,34 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   } else {
     BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)in_rows * k, &Bd));
   }
+  const int world = dist_b ? comm_world(ctx) : 1, rank = comm_rank(ctx);
   if (b_dev != nullptr) {
     // nothing to upload
+  } else if (dist_b && world > 1) {
+    // bof_dist_csrmm: B is replicated over the ranks.  Every rank uploads rows [r0, r1) of it (1/world of the PCIe
+    // traffic) and the slices are exchanged over NVLink on the collective stream; meanwhile this rank's first A
+    // blocks already upload behind the slice.  The SpMM gathers arbitrary rows of B, so it waits for all of it.
+    auto shard = [&](int r, int64_t* r0, int64_t* r1) {
+      const int64_t base = in_rows / world, rem = in_rows % world;
+      *r0 = r * base + std::min<int64_t>(r, rem);
+      *r1 = *r0 + base + (r < rem ? 1 : 0);
+    };
+    int64_t r0, r1;
+    shard(rank, &r0, &r1);
+    BOF_TRY(copy1d(ctx, Bd + r0 * k, b + r0 * k, (size_t)(r1 - r0) * k * 4, H2D, ctx->h2d));
+    cudaEvent_t ev_own = get_event(ctx, 1);
+    BOF_CUDA(ctx, cudaEventRecord(ev_own, ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->coll, ev_own, 0));
+    trace_mark(ctx, ctx->h2d, "h2d: own slice of the dense operand landed", rank);
+    for (int src = 0; src < world; ++src) {
+      int64_t s0, s1;
+      shard(src, &s0, &s1);
+      if (s1 > s0) BOF_TRY(comm_broadcast_f32(ctx, Bd + s0 * k, (size_t)(s1 - s0) * k, src));
+    }
+    cudaEvent_t evB = get_event(ctx, 0);
+    BOF_CUDA(ctx, cudaEventRecord(evB, ctx->coll));
+    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
+    trace_mark(ctx, ctx->coll, "coll: dense operand complete on this rank", 0);
   } else if (colmaj) {
     float* Braw = nullptr;
     BOF_TRY(slot_reserve(ctx, S_DENSE_T, (size_t)in_rows * k, &Braw));
@@ -223,6 +249,11 @@ int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, float alp
                         const int64_t* ia, const int64_t* ja, const float* b_dev, float* c) {
   if (ctx && b_dev == nullptr) return fail(ctx, BOF_EINVAL, "csrmm_devb: b_dev is null");
   return host_csrmm_impl(ctx, 'N', m, n, k, alpha, beta, a, ia, ja, 'R', nullptr, c, b_dev);
+}
+
+int bof_dist_csrmm(bof_ctx* ctx, int64_t m_local, int64_t n, int64_t k, float alpha, float beta, const float* a,
+                   const int64_t* ia, const int64_t* ja, const float* b, float* c_local) {
+  return host_csrmm_impl(ctx, 'N', m_local, n, k, alpha, beta, a, ia, ja, 'R', b, c_local, nullptr, true);
 }
 
 // flash::csrgemv: x resident, A streams in row blocks; 'N' writes disjoint y rows, 'T' accumulates

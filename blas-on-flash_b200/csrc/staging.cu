@@ -512,6 +512,7 @@ int drain_wait(bof_ctx* ctx) {
 int sync_all(bof_ctx* ctx) {
   if (ctx->drainer) ctx->drainer->wait_all_issued();  // the drainer may still be enqueueing copies on the streams
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
+  if (ctx->coll) BOF_CUDA(ctx, cudaStreamSynchronize(ctx->coll));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
   return drain_wait(ctx);
@@ -522,6 +523,7 @@ int sync_all(bof_ctx* ctx) {
 void quiesce(bof_ctx* ctx) {
   if (ctx->drainer) ctx->drainer->wait_all_issued();
   cudaStreamSynchronize(ctx->h2d);
+  if (ctx->coll) cudaStreamSynchronize(ctx->coll);
   cudaStreamSynchronize(ctx->compute);
   cudaStreamSynchronize(ctx->d2h);
   if (ctx->drainer) ctx->drainer->wait_idle();

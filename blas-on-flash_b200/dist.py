@@ -42,12 +42,38 @@ def as_tensor(ptr: int, count: int, device: int):
     return torch.as_tensor(DeviceView(ptr, count), device=f"cuda:{device}")
 
 
+def init_comm(ctx, group=None):
+    """Give `ctx` a communicator rank of its own (bof_comm_init): rank 0 creates the NCCL id, torch.distributed
+    carries the 128 bytes, the library then runs its collectives (panel broadcasts of the replicated operand, the
+    k-means allreduce) on its own streams -- no host synchronisation between the exchange and the kernels."""
+    import torch
+    import torch.distributed as dist
+
+    from . import comm_unique_id
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return False
+    if ctx.comm_world() > 1:
+        return True
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    raw = comm_unique_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(raw), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0, group=group)
+    ctx.comm_init(world, rank, bytes(t.cpu().tolist()))
+    return True
+
+
 def lloyd(km, iters: int, group=None):
     """`iters` Lloyd iterations on this rank's resident shard; with a process group the partial
     [K*dim sums | K counts] buffer is summed in place over NVLink by NCCL on the library's stream."""
     import torch
     import torch.distributed as dist
 
+    if km.ctx.comm_world() > 1:   # the context has its own communicator: the library allreduces on its stream
+        km.lloyd(iters)
+        return
     use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     stream = torch.cuda.ExternalStream(km.stream(), device=km.ctx.device) if use_dist else None
     for _ in range(iters):

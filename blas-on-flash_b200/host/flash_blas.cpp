@@ -18,6 +18,15 @@ Callback dummy_std_func = [] {};
 namespace {
 std::mutex g_mu;
 bof_ctx* g_ctx = nullptr;
+bof_mgpu* g_mgpu = nullptr;   // BOF_GPUS > 1: one context per GPU in this process, g_ctx = its rank 0
+
+// BOF_GPUS=<n> | all : spread gemm / csrmm / csrgemv / kmeans_lloyd over the GPUs of the node (default: one GPU)
+int env_gpus() {
+  const char* v = std::getenv("BOF_GPUS");
+  if (!v) return 1;
+  if (std::string(v) == "all") return 0;
+  return std::max(1, std::atoi(v));
+}
 
 int env_device() {
   for (const char* name : {"BOF_DEVICE", "LOCAL_RANK"})
@@ -39,13 +48,25 @@ bof_csr* find_pinned(flash_ptr<FPTYPE> a, flash_ptr<MKL_INT> ia, flash_ptr<MKL_I
 
 FBLAS_INT done(const char* what, int rc) {
   if (rc == 0) return 0;
-  std::fprintf(stderr, "[flash::%s] %s\n", what, g_ctx ? bof_last_error(g_ctx) : bof_last_error(nullptr));
+  const char* msg = g_ctx ? bof_last_error(g_ctx) : bof_last_error(nullptr);
+  if (g_mgpu && bof_mgpu_last_error(g_mgpu)[0]) msg = bof_mgpu_last_error(g_mgpu);
+  std::fprintf(stderr, "[flash::%s] %s\n", what, msg);
   return -1;
 }
+bool multi() { return g_mgpu != nullptr && bof_mgpu_count(g_mgpu) > 1; }
 }  // namespace
 
 bof_ctx* flash_context() {
   std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ctx == nullptr && env_gpus() != 1) {
+    bof_config cfg{};
+    if (bof_mgpu_create(&cfg, env_gpus(), nullptr, &g_mgpu) == 0) {
+      g_ctx = bof_mgpu_ctx(g_mgpu, 0);
+    } else {
+      std::fprintf(stderr, "[flash] cannot create the multi-GPU context (%s); falling back to one GPU\n", bof_last_error(nullptr));
+      g_mgpu = nullptr;
+    }
+  }
   if (g_ctx == nullptr) {
     bof_config cfg{};
     cfg.device = env_device();
@@ -67,7 +88,9 @@ void flash_destroy() {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_pinned) bof_csr_close(kv.second.h);
   g_pinned.clear();
-  if (g_ctx) bof_ctx_destroy(g_ctx);
+  if (g_mgpu) bof_mgpu_destroy(g_mgpu);   // owns g_ctx
+  else if (g_ctx) bof_ctx_destroy(g_ctx);
+  g_mgpu = nullptr;
   g_ctx = nullptr;
 }
 
@@ -76,6 +99,9 @@ FBLAS_INT gemm(CHAR mat_ord, CHAR trans_a, CHAR trans_b, FBLAS_UINT m, FBLAS_UIN
                FBLAS_UINT lda_b, FBLAS_UINT lda_c) {
   bof_ctx* ctx = flash_context();
   if (!ctx) return -1;
+  if (multi())
+    return done("gemm", bof_mgpu_gemm(g_mgpu, mat_ord, trans_a, trans_b, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta, a.ptr,
+                                      b.ptr, c.ptr, (int64_t)lda_a, (int64_t)lda_b, (int64_t)lda_c));
   return done("gemm", bof_host_gemm(ctx, mat_ord, trans_a, trans_b, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta,
                                     a.ptr, b.ptr, c.ptr, (int64_t)lda_a, (int64_t)lda_b, (int64_t)lda_c));
 }
@@ -105,6 +131,10 @@ FBLAS_INT csrmm(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, FBLAS_UINT k, FPTYPE a
   if (!ctx) return -1;
   if (bof_csr* h = find_pinned(a, ia, ja, m, n))
     return done("csrmm", bof_csr_mm(h, trans_a, (int64_t)k, alpha, beta, ord_b, b, c));
+  if (multi())
+    return done("csrmm", bof_mgpu_csrmm(g_mgpu, trans_a, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta, a.ptr,
+                                        reinterpret_cast<const int64_t*>(ia.ptr), reinterpret_cast<const int64_t*>(ja.ptr),
+                                        ord_b, b, c));
   return done("csrmm", bof_host_csrmm(ctx, trans_a, (int64_t)m, (int64_t)n, (int64_t)k, alpha, beta, a.ptr,
                                       reinterpret_cast<const int64_t*>(ia.ptr),
                                       reinterpret_cast<const int64_t*>(ja.ptr), ord_b, b, c));
@@ -125,6 +155,9 @@ FBLAS_INT csrgemv(CHAR trans_a, FBLAS_UINT m, FBLAS_UINT n, flash_ptr<FPTYPE> a,
   bof_ctx* ctx = flash_context();
   if (!ctx) return -1;
   if (bof_csr* h = find_pinned(a, ia, ja, m, n)) return done("csrgemv", bof_csr_mv(h, trans_a, b, c));
+  if (multi())
+    return done("csrgemv", bof_mgpu_csrgemv(g_mgpu, trans_a, (int64_t)m, (int64_t)n, a.ptr, reinterpret_cast<const int64_t*>(ia.ptr),
+                                            reinterpret_cast<const int64_t*>(ja.ptr), b, c));
   return done("csrgemv", bof_host_csrgemv(ctx, trans_a, (int64_t)m, (int64_t)n, a.ptr,
                                           reinterpret_cast<const int64_t*>(ia.ptr),
                                           reinterpret_cast<const int64_t*>(ja.ptr), b, c));
@@ -162,6 +195,10 @@ FBLAS_INT kmeans_lloyd(flash_ptr<FPTYPE> points, flash_ptr<FPTYPE> centers, FBLA
                        kmeans_allreduce_fn allreduce, void* allreduce_user) {
   bof_ctx* ctx = flash_context();
   if (!ctx) return -1;
+  static_assert(sizeof(FBLAS_UINT) == sizeof(int64_t), "assignment buffer is 64-bit");
+  if (multi() && allreduce == nullptr)   // this process drives several GPUs: the library shards and allreduces itself
+    return done("kmeans_lloyd", bof_mgpu_kmeans_lloyd(g_mgpu, (int64_t)npoints, (int64_t)ncenters, (int64_t)ndims, points.ptr,
+                                                      centers.ptr, (int64_t)n_iters, reinterpret_cast<int64_t*>(closest_center)));
   bof_kmeans* km = nullptr;
   int rc = bof_kmeans_open(ctx, (int64_t)npoints, (int64_t)ncenters, (int64_t)ndims, points.ptr, centers.ptr, &km);
   for (FBLAS_UINT it = 0; rc == 0 && it < n_iters; ++it) {
@@ -176,7 +213,6 @@ FBLAS_INT kmeans_lloyd(flash_ptr<FPTYPE> points, flash_ptr<FPTYPE> centers, FBLA
     if (rc == 0) rc = bof_kmeans_update(km);
   }
   if (rc == 0) {
-    static_assert(sizeof(FBLAS_UINT) == sizeof(int64_t), "assignment buffer is 64-bit");
     rc = bof_kmeans_get(km, centers.ptr, reinterpret_cast<int64_t*>(closest_center));
   }
   if (km) bof_kmeans_close(km);

@@ -217,6 +217,56 @@ BOF_API int bof_host_csrmm_devb(bof_ctx* ctx, int64_t m, int64_t n, int64_t k, f
                         const float* a, const int64_t* ia, const int64_t* ja, const float* b_dev,
                         float* c);
 
+/* ---- multi-GPU: one communicator rank per context (north_star (5)) ---------------
+ * The reference is single-process, single-node, CPU only: there is nothing to replace; these entry
+ * points are how its row-block tasks (src/blas/csrmm.cpp:64-126, src/blas/gemm.cpp:83-129) spread over the GPUs
+ * of a node.  Output row blocks are sharded over the ranks with no collective on the compute path; NVLink carries
+ * (i) the replicated dense operand, uploaded 1/world per rank and broadcast panel by panel while the tensor cores
+ * / SpMM already work on what has arrived, and (ii) the k-means allreduce of centroid sums and counts.
+ * NCCL is dlopen'ed on first use (libnccl.so.2): no link-time dependency, never loaded by single-GPU users.
+ *   one process per GPU: rank 0 calls bof_comm_unique_id, the launcher distributes the 128 bytes, every rank calls
+ *                        bof_comm_init on its context;
+ *   one process, many GPUs: bof_mgpu_create below. */
+#define BOF_COMM_ID_BYTES 128
+BOF_API int bof_comm_unique_id(void* id_out /* BOF_COMM_ID_BYTES */);
+BOF_API int bof_comm_init(bof_ctx* ctx, int world, int rank, const void* id);
+BOF_API int bof_comm_finalize(bof_ctx* ctx);
+BOF_API int bof_comm_world(const bof_ctx* ctx);   /* 1 without a communicator */
+BOF_API int bof_comm_rank(const bof_ctx* ctx);
+/* flash::gemm, row-major, on this rank's rows of op(A) and C (m_local of them); `b` is the WHOLE B in host memory
+ * every rank can read (same contents on all ranks).  Collective: every rank of the communicator calls it with the
+ * same n, k, tb.  Panel j of B is uploaded by rank j % world and broadcast; C leaves column slab by column slab. */
+BOF_API int bof_dist_gemm(bof_ctx* ctx, char ta, char tb, int64_t m_local, int64_t n, int64_t k, float alpha,
+                  float beta, const float* a_local, const float* b, float* c_local, int64_t lda,
+                  int64_t ldb, int64_t ldc);
+/* flash::csrmm('N', ..., 'R', ...) on this rank's row block of A (offsets may be un-rebased: values / indices are
+ * addressed relative to ia[0]) and of C; `b` is the whole n x k B in host memory.  Collective. */
+BOF_API int bof_dist_csrmm(bof_ctx* ctx, int64_t m_local, int64_t n, int64_t k, float alpha, float beta,
+                   const float* a, const int64_t* ia, const int64_t* ja, const float* b, float* c_local);
+
+/* One process, several GPUs (what flash_setup() + the flash:: entry points use when BOF_GPUS > 1): a context and a
+ * communicator rank per device, one host thread per device inside every call, host operands shared by all of them
+ * (one copy of B in host memory instead of one per process).  ndev <= 0: every visible device; devices may be NULL
+ * (ordinals 0 .. ndev-1); cfg->device is ignored.  Same one-call-at-a-time rule as a single context. */
+typedef struct bof_mgpu bof_mgpu;
+BOF_API int bof_mgpu_create(const bof_config* cfg, int ndev, const int* devices, bof_mgpu** out);
+BOF_API int bof_mgpu_destroy(bof_mgpu* mg);
+BOF_API int bof_mgpu_count(const bof_mgpu* mg);
+BOF_API bof_ctx* bof_mgpu_ctx(bof_mgpu* mg, int rank);
+BOF_API const char* bof_mgpu_last_error(const bof_mgpu* mg);
+/* flash::gemm: rows of C ('R') / columns of C ('C') sharded over the GPUs, the other operand panel-broadcast. */
+BOF_API int bof_mgpu_gemm(bof_mgpu* mg, char ord, char ta, char tb, int64_t m, int64_t n, int64_t k, float alpha,
+                  float beta, const float* a, const float* b, float* c, int64_t lda, int64_t ldb, int64_t ldc);
+/* flash::csrmm: trans_a='N', ord_b='R' = nnz-balanced row blocks per GPU; every other combination runs on GPU 0. */
+BOF_API int bof_mgpu_csrmm(bof_mgpu* mg, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
+                   const float* a, const int64_t* ia, const int64_t* ja, char ord_b, const float* b, float* c);
+/* flash::csrgemv: 'N' disjoint row blocks; 'T' per-GPU partial y added on the host in GPU order (deterministic). */
+BOF_API int bof_mgpu_csrgemv(bof_mgpu* mg, char trans_a, int64_t m, int64_t n, const float* a, const int64_t* ia,
+                     const int64_t* ja, const float* x, float* y);
+/* drivers/in_mem_kmeans.cpp:89-152 x iters: points sharded and resident, NCCL allreduce per iteration. */
+BOF_API int bof_mgpu_kmeans_lloyd(bof_mgpu* mg, int64_t npoints, int64_t ncenters, int64_t dim,
+                          const float* points_host, float* centers_host, int64_t iters, int64_t* assign_out);
+
 /* flash::kmeans, the distance tile of k-means (include/flash_blas.h:20-25; KMeansTask::execute,
  * include/tasks/kmeans_task.h:53-82): the product of bof_host_gemm, then C(i, j) += c_l2sq[i] and
  * C(i, j) += p_l2sq[j] in that order (i over m, j over n), applied to each output block on the device
@@ -259,7 +309,8 @@ BOF_API int bof_csr_close(bof_csr* h);
 /* One Lloyd iteration on this rank's shard of the points, device-resident across calls:
  * bof_kmeans_open uploads the shard once (drivers/kmeans.cpp:206-217: points mapped, norms
  * computed once); bof_kmeans_local_step = closest_centers + per-cluster partial sums
- * (drivers/in_mem_kmeans.cpp:69-125) leaving [K*dim sums | K counts] fp32 in a device buffer
+ * (drivers/in_mem_kmeans.cpp:69-125) leaving [K*dim sums | K (count & 4095) | K (count >> 12)] fp32 -- every entry
+ * an exact integer or sum, also after adding the ranks' buffers -- in a device buffer
  * whose address is returned so that the caller can NCCL-allreduce it in place (the only
  * collective on the path); bof_kmeans_update divides and refreshes the resident centers.
  * assign_out (host, int64 as FBLAS_UINT center_index, in_mem_kmeans.cpp:82-85) may be NULL. */
@@ -268,6 +319,10 @@ BOF_API int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int
                     const float* points_host, const float* centers_host, bof_kmeans** out);
 BOF_API int bof_kmeans_local_step(bof_kmeans* km, void** dev_partial, size_t* partial_floats);
 BOF_API int bof_kmeans_update(bof_kmeans* km);
+/* In-place NCCL sum of the partial buffer over the ranks of the context's communicator, on the k-means stream (the
+ * only reduction on the path); no-op at world 1.  bof_kmeans_lloyd = iters x (local_step, allreduce, update). */
+BOF_API int bof_kmeans_allreduce(bof_kmeans* km);
+BOF_API int bof_kmeans_lloyd(bof_kmeans* km, int64_t iters);
 BOF_API int bof_kmeans_get(bof_kmeans* km, float* centers_host, int64_t* assign_host);
 BOF_API void* bof_kmeans_stream(bof_kmeans* km);
 BOF_API int bof_kmeans_close(bof_kmeans* km);

@@ -1,0 +1,117 @@
+"""GPU parity of the multi-GPU paths (needs >= 2 GPUs; skipped on a single-GPU box): one process driving several
+GPUs through bof_mgpu_* (what the C++ flash:: adapters use with BOF_GPUS > 1), and one process per GPU under
+torchrun through bof_comm_init + bof_dist_* (tools/dist_check.py).  World-size-1 behaviour of the same entry points
+is covered on any GPU box."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+TOL = 1e-5
+NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
+need2 = pytest.mark.skipif(NGPU < 2, reason="needs at least 2 GPUs")
+
+
+def test_dist_entry_points_at_world_one(bof, ctx):
+    """without a communicator bof_dist_* are the plain pipelines and bof_kmeans_allreduce is a no-op"""
+    assert ctx.comm_world() == 1
+    M, N, K = 700, 500, 900
+    a, b = oracle.gen_dense((M, K), seed=1), oracle.gen_dense((K, N), seed=2)
+    c = np.full((M, N), np.nan, np.float32)
+    ctx.dist_gemm("N", "N", M, N, K, 1.0, 0.0, a, b, c)
+    assert oracle.rel_fro(c, oracle.gemm("R", "N", "N", M, N, K, 1.0, 0.0, a, b, np.zeros_like(c), acc64=True)) <= TOL
+    m, n, k = 3000, 2000, 64
+    av, ia, ja = oracle.gen_csr(m, n, 16, seed=3)
+    B = oracle.gen_dense((n, k), seed=4)
+    C = np.full((m, k), np.nan, np.float32)
+    ctx.dist_csrmm(m, n, k, 1.0, 0.0, av, ia, ja, B, C)
+    assert oracle.rel_fro(C, oracle.csrmm("N", m, n, k, 1.0, 0.0, av, ia, ja, "R", B, np.zeros_like(C), acc64=True)) <= TOL
+
+
+def test_slab_download_path_small_m(ctx):
+    """M small enough that every row block rides in the panel prologue: C leaves the device slab by slab"""
+    M, N, K = 1024, 40960, 2048     # B = 320 MiB -> panelled; one row block
+    a, b = oracle.gen_dense((M, K), seed=5), oracle.gen_dense((K, N), seed=6)
+    c0 = oracle.gen_dense((M, N), seed=7)
+    c = c0.copy()
+    ctx.host_gemm("R", "N", "N", M, N, K, 1.0, 0.5, a, b, c)
+    jj = np.random.default_rng(1).integers(0, N, 512)
+    ref = a.astype(np.float64) @ b[:, jj].astype(np.float64) + 0.5 * c0[:, jj]
+    assert np.linalg.norm(c[:, jj] - ref) / np.linalg.norm(ref) <= TOL
+
+
+def test_kmeans_count_split_is_exact(bof, ctx):
+    """cluster sizes travel as (size & 4095, size >> 12): the centroid of a cluster of > 4096 points is exact"""
+    P, K, d = 20000, 3, 8
+    pts = np.zeros((P, d), np.float32); pts[:, 0] = 1.0
+    pts[15000:, 0] = 100.0
+    c0 = np.array([[1.0] + [0] * (d - 1), [100.0] + [0] * (d - 1), [1000.0] + [0] * (d - 1)], np.float32)
+    km = bof.KMeans(ctx, P, K, d, pts, c0)
+    km.lloyd(2)
+    c = np.zeros((K, d), np.float32); a = np.zeros(P, np.int64)
+    km.get(c, a); km.close()
+    assert np.allclose(c, c0 * np.array([[1], [1], [0]], np.float32), rtol=1e-6, atol=0)   # 15000 and 5000 points; empty cluster -> 0
+    assert (a[:15000] == 0).all() and (a[15000:] == 1).all()
+
+
+@need2
+def test_mgpu_one_process(bof):
+    n_use = min(NGPU, 4)
+    with bof.MultiGpu(ndev=n_use) as mg:
+        assert mg.count() == n_use
+        for o, ta, tb in (("R", "N", "N"), ("R", "T", "N"), ("C", "N", "T"), ("R", "N", "T")):
+            M, N, K = 2100, 1700, 1300
+            ar, ac = (M, K) if ta == "N" else (K, M)
+            br, bc = (K, N) if tb == "N" else (N, K)
+            cr, cc = M, N
+            if o == "C":
+                ar, ac, br, bc, cr, cc = ac, ar, bc, br, cc, cr
+            a, b, c0 = oracle.gen_dense((ar, ac), seed=1), oracle.gen_dense((br, bc), seed=2), oracle.gen_dense((cr, cc), seed=3)
+            c = c0.copy()
+            mg.gemm(o, ta, tb, M, N, K, 1.5, 0.5, a, b, c)
+            assert oracle.rel_fro(c, oracle.gemm(o, ta, tb, M, N, K, 1.5, 0.5, a, b, c0, acc64=True)) <= TOL, (o, ta, tb)
+        m, n, k = 60000, 45000, 128
+        av, ia, ja = oracle.gen_csr(m, n, 20, seed=4)
+        B, C0 = oracle.gen_dense((n, k), seed=5), oracle.gen_dense((m, k), seed=6)
+        C = C0.copy()
+        mg.csrmm("N", m, n, k, 1.25, 0.75, av, ia, ja, "R", B, C)
+        assert oracle.rel_fro(C, oracle.csrmm("N", m, n, k, 1.25, 0.75, av, ia, ja, "R", B, C0, acc64=True)) <= TOL
+        x, xt = oracle.gen_dense((n,), seed=7), oracle.gen_dense((m,), seed=8)
+        y = np.full(m, np.nan, np.float32)
+        mg.csrgemv("N", m, n, av, ia, ja, x, y)
+        assert oracle.rel_fro(y, oracle.csrgemv("N", m, n, av, ia, ja, x, acc64=True)) <= TOL
+        yt = np.full(n, np.nan, np.float32)
+        mg.csrgemv("T", m, n, av, ia, ja, xt, yt)
+        assert oracle.rel_fro(yt, oracle.csrgemv("T", m, n, av, ia, ja, xt, acc64=True)) <= TOL
+        yt2 = np.full(n, np.nan, np.float32)
+        mg.csrgemv("T", m, n, av, ia, ja, xt, yt2)
+        assert oracle.rel_fro(yt2, yt) <= 1e-6
+        rng = np.random.default_rng(9)
+        Kc, d, P = 32, 24, 40000
+        mu = (rng.normal(size=(Kc, d)) * 4).astype(np.float32)
+        pts = (mu[rng.integers(0, Kc, P)] + 0.3 * rng.normal(size=(P, d))).astype(np.float32)
+        c0 = (mu + 0.05 * rng.normal(size=(Kc, d))).astype(np.float32)
+        cent = c0.copy(); asg = np.zeros(P, np.int64)
+        mg.kmeans_lloyd(P, Kc, d, pts, cent, 3, asg)
+        c = c0.copy()
+        for _ in range(3):
+            c, a_ref, _ = oracle.lloyd_iter(pts, c)
+        assert oracle.rel_fro(cent, c) <= TOL
+
+
+@need2
+def test_dist_paths_under_torchrun():
+    n = min(NGPU, 4)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(ROOT / "tools" / "dist_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"comm_world": %d' % n in r.stdout

@@ -241,21 +241,18 @@ def csrmm_cfg3(env: Env, scale=1.0):
                   "api": "bof_host_csrmm, pinned host buffers, B uploaded by every rank (replicated)"}
     par["rel_fro_sampled_rows_e2e"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
     if world > 1:
-        # every rank uploads 1/N of B, NVLink all-gather, then the row-block pipeline on the device copy
+        # SURVEY 8(f)-1 behind the C ABI: every rank uploads 1/N of B's rows, the slices are broadcast over NVLink on the
+        # library's collective stream while this rank's first A blocks upload, then the row-block pipeline runs
         from bof_b200 import dist as bdist
-        Bdev = torch.empty((n, k), device=env.dev)
-
-        def step():
-            up = bdist.allgather_dense(B_h, Bdev)
-            ctx.host_csrmm_devb(mr, n, k, 1.0, 0.0, a_h, ia_h, ja_h, Bdev, C_h)
-            return up
-        tg = env.time_wall(step, iters=2, warm=1)
+        bdist.init_comm(ctx)
+        C_h.zero_()
+        tg = env.time_wall(lambda: ctx.dist_csrmm(mr, n, k, 1.0, 0.0, a_h, ia_h, ja_h, B_h, C_h), iters=2, warm=1)
         st = ctx.stats()
-        rec["e2e_allgather"] = {"value": 2.0 * nnz * k / tg / 1e9, "unit": "GFLOP/s", "ms": tg * 1e3,
-                                "h2d_bytes_per_step": st.h2d_bytes + n * k * 4 // world, "d2h_bytes_per_step": st.d2h_bytes,
-                                "api": "B slice H2D + NCCL all-gather over NVLink, then bof_host_csrmm_devb"}
-        par["rel_fro_sampled_rows_allgather"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
-        del Bdev
+        rec["e2e_shared_b"] = {"value": 2.0 * nnz * k / tg / 1e9, "unit": "GFLOP/s", "ms": tg * 1e3,
+                               "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
+                               "h2d_gbs_per_gpu": st.h2d_bytes / tg / 1e9,
+                               "api": "bof_dist_csrmm: 1/N of B H2D per rank + NCCL broadcasts over NVLink, then the row-block pipeline"}
+        par["rel_fro_sampled_rows_shared_b"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
     if env.cpu:
         try:
             from oracle import mkl
