@@ -138,6 +138,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   int64_t rb = (int64_t)ctx->cfg.gemm_row_block;
   rb = std::max<int64_t>(256, round_up<int64_t>(rb, 256));
   rb = std::min(rb, round_up<int64_t>(cn.Mo, 256));
+  // a rank's shard of a multi-GPU job can be a single block: cut it into four so that the first MMAs start after a
+  // quarter of it has landed and the C slabs leave earlier
+  if (dist_q && comm_world(ctx) > 1 && cn.Mo <= 4 * rb) rb = std::max<int64_t>(1024, round_up<int64_t>(ceil_div<int64_t>(cn.Mo, 4), 256));
   const int nblk = (int)ceil_div<int64_t>(cn.Mo, rb);
   const size_t pb = plane_bytes(rb, kp);
   constexpr int NB = kGemmRing;
@@ -351,12 +354,15 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
       BOF_CUDA(ctx, cudaEventRecord(ev, ctx->compute));
       for (int i = 0; i < older; ++i) BOF_TRY(fetch_slab(i, n0, n1, ev));      // panel t of the earlier blocks
       if (t < npro) BOF_TRY(fetch_slab(t, 0, n1, ev));                          // panels 0..t of block t
+      if (slab_ticket == 0) trace_mark(ctx, ctx->d2h, "d2h: slabs of panel downloaded", t);
     } else if (t == n_qpan - 1) {
       for (int i = 0; i < npro; ++i) BOF_TRY(finish_block(i));
     }
   }
   if (slab_download) {
+    trace_host(ctx, "caller: everything issued", 0);
     BOF_TRY(sync_all(ctx));
+    trace_host(ctx, "caller: sync_all returned", 0);
     trace_dump(ctx, "bof_host_gemm");
     stats_end(ctx);
     return call_guard.done();

@@ -27,6 +27,29 @@ __device__ __forceinline__ void fma4(float4& acc, float v, const float4& b) {
   acc.w = fmaf(v, b.w, acc.w);
 }
 
+// ---- row splitting (north_star (1): "row-split / merge-path ... warp-per-row segments") ------------------------
+// A row group (4..32 lanes) per row is the right shape for the short rows of the BASELINE matrices, but a power-law
+// matrix has rows with 10^4..10^6 nonzeros, and one warp walking such a row would outlast the rest of the launch.
+// The row kernel therefore only DEFERS them: rows longer than kMidRow go to a list (atomic append -- integer
+// bookkeeping only; no floating-point value ever passes through an atomic) and a second, persistent kernel splits
+// each of them into 32-nonzero segments over
+//   * the 8 warps of one block (rows up to the long threshold), partial sums combined through shared memory in
+//     warp order, or
+//   * every warp of the grid (rows beyond max(16384, 64 x the mean row length)), block partials combined through a
+//     fixed workspace in block order after a grid barrier (all blocks are co-resident),
+// so the result is deterministic and no row occupies one warp for more than kMidRow nonzeros.  No host round trip,
+// no size-dependent workspace; a matrix without such rows pays one memset and one empty launch.
+constexpr int kMidRow = 1024;            // nonzeros above which a row leaves the row-group kernel
+constexpr int kLongRowMin = 16384;       // rows above max(this, kLongRowFactor x mean) are spread over the whole grid
+constexpr int kLongRowFactor = 64;
+constexpr int kLongCap = 4096;           // rows the grid-wide path takes per launch (more spill into the block path)
+
+struct LongRows {
+  uint32_t* counters;   // [0] rows in mid_list, [1] rows in long_list, [2..3] grid barrier, [4] work ticket
+  int32_t* mid_list;
+  int32_t* long_list;
+};
+
 // L lanes per row, KV float4 per lane: one pass covers 4*L*KV columns starting at
 // blockIdx.y * 4*L*KV.  Requires B, C 16-byte aligned, ldb/ldc multiples of 4; the column
 // tail (k not a multiple of 4*L) is masked per float4, k itself must be a multiple of 4.
@@ -37,7 +60,7 @@ __global__ void __launch_bounds__(256, MINB)
 spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
                        const int32_t* __restrict__ idx, const int64_t* __restrict__ offs,
                        const float* __restrict__ B, int64_t ldb, float beta, float* __restrict__ C,
-                       int64_t ldc) {
+                       int64_t ldc, const LongRows lr) {
   constexpr int ROWS_PER_WARP = 32 / L;
   const int lane = threadIdx.x & 31;
   const int sub = lane / L;       // which row of the warp
@@ -46,13 +69,28 @@ spmm_csr_rm_vec_kernel(int64_t m, int64_t k, float alpha, const float* __restric
   const int64_t row = warp_global * ROWS_PER_WARP + sub;
   const int64_t col0 = (int64_t)blockIdx.y * (4 * L * KV) + 4 * sl;
   const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
-  const bool row_ok = row < m;
+  bool row_ok = row < m;
 
   const int64_t base = offs[0];
   int64_t beg = 0, end = 0;
   if (row_ok) {
     beg = offs[row] - base;
     end = offs[row + 1] - base;
+  }
+  if (lr.counters != nullptr && end - beg > kMidRow) {
+    // deferred to spmm_long_rows_kernel: every column chunk skips the row, chunk 0 files it.  The lists cannot
+    // overflow (mid_list has m entries; a full long_list spills into mid_list, whose path handles any length).
+    if (sl == 0 && blockIdx.y == 0) {
+      const int64_t mean = (offs[m] - base) / m;
+      bool is_long = end - beg > max((int64_t)kLongRowMin, (int64_t)kLongRowFactor * mean);
+      if (is_long) {
+        const uint32_t got = atomicAdd(&lr.counters[1], 1u);
+        if (got < (uint32_t)kLongCap) lr.long_list[got] = (int32_t)row; else is_long = false;
+      }
+      if (!is_long) lr.mid_list[atomicAdd(&lr.counters[0], 1u)] = (int32_t)row;
+    }
+    end = beg;
+    row_ok = false;
   }
 
   bool col_ok[KV];
@@ -269,6 +307,172 @@ spmm_csr_rm_tma_kernel(int64_t m, int64_t k, float alpha, const float* __restric
   }
 }
 
+
+// ---- deferred (long) rows ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all blocks of the (co-resident) grid meet; cnt / gen live in global memory, zero before the launch
+__device__ __forceinline__ void grid_barrier(uint32_t* cnt, uint32_t* gen, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t g = ld_acquire_u32(gen);
+    __threadfence();
+    if (atomicAdd(cnt, 1u) == nblocks - 1) {
+      atomicExch(cnt, 0u);
+      __threadfence();
+      atomicAdd(gen, 1u);
+    } else {
+      while (ld_acquire_u32(gen) == g) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr int LR_WARPS = 8;
+
+// Partial sums of the 32-nonzero segments seg0, seg0 + stride, ... of one row, for columns [c0, c0 + 128 KV):
+// lane l holds float4 columns c0 + 4 l + 128 v.  U rows of B in flight per warp.
+template <int KV>
+__device__ __forceinline__ void row_segments(int64_t beg, int64_t end, int64_t seg0, int64_t stride, int64_t c0, int64_t k,
+                                             const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                                             const float* __restrict__ B, int64_t ldb, float4 (&acc)[KV]) {
+  constexpr int U = KV == 1 ? 8 : (KV == 2 ? 4 : 2);   // B rows in flight per warp
+  const int lane = threadIdx.x & 31;
+  bool col_ok[KV];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    col_ok[v] = c0 + 4 * lane + 128 * v < k;
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t nseg = (end - beg + 31) / 32;
+  for (int64_t sg = seg0; sg < nseg; sg += stride) {
+    const int64_t j = beg + sg * 32;
+    const int64_t mine = j + lane;
+    int32_t c = 0;
+    float a = 0.f;
+    if (mine < end) {
+      c = __ldcs(idx + mine);
+      a = __ldcs(vals + mine);
+    }
+    const int cnt = (int)min((int64_t)32, end - j);
+    for (int t = 0; t < cnt; t += U) {
+      int32_t cc[U];
+      float aa[U];
+      float4 bb[U][KV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {   // t, u, cnt are warp-uniform
+        cc[u] = __shfl_sync(0xffffffffu, c, (t + u) & 31);
+        aa[u] = __shfl_sync(0xffffffffu, a, (t + u) & 31);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool live = t + u < cnt;   // past the end of the segment nothing is read (0 * Inf would poison the sum)
+        const float* brow = B + (int64_t)(live ? cc[u] : 0) * ldb + c0 + 4 * lane;
+        if (!live) aa[u] = 0.f;
+#pragma unroll
+        for (int v = 0; v < KV; ++v) bb[u][v] = (live && col_ok[v]) ? ldg_f4(brow + 128 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < KV; ++v) fma4(acc[v], aa[u], bb[u][v]);
+    }
+  }
+}
+
+// Persistent kernel over the rows the row-group kernel deferred (see LongRows above).  red: LR_WARPS x 128 KV floats.
+template <int KV>
+__global__ void __launch_bounds__(LR_WARPS * 32)
+spmm_long_rows_kernel(int64_t k, float alpha, const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                      const int64_t* __restrict__ offs, const float* __restrict__ B, int64_t ldb, float beta,
+                      float* __restrict__ C, int64_t ldc, const LongRows lr, float* __restrict__ partial_ws) {
+  constexpr int CW = 128 * KV;   // columns per pass
+  __shared__ __align__(16) float red[LR_WARPS][CW];
+  __shared__ uint32_t ticket_s;
+  const uint32_t n_mid = lr.counters[0], n_long = min(lr.counters[1], (uint32_t)kLongCap);
+  if (n_mid == 0 && n_long == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = offs[0];
+  const unsigned G = gridDim.x;
+
+  auto stash = [&](const float4 (&acc)[KV]) {
+#pragma unroll
+    for (int v = 0; v < KV; ++v) *reinterpret_cast<float4*>(&red[warp][4 * lane + 128 * v]) = acc[v];
+  };
+
+  // ---- rows split over the warps of one block: blocks draw rows from a ticket counter
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_s = atomicAdd(&lr.counters[4], 1u);
+    __syncthreads();
+    const uint32_t t = ticket_s;
+    if (t >= n_mid) break;
+    const int64_t row = lr.mid_list[t];
+    const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+    for (int64_t c0 = 0; c0 < k; c0 += CW) {
+      float4 acc[KV];
+      row_segments<KV>(beg, end, warp, LR_WARPS, c0, k, vals, idx, B, ldb, acc);
+      __syncthreads();   // red free again
+      stash(acc);
+      __syncthreads();
+      for (int c = threadIdx.x; c < CW && c0 + c < k; c += LR_WARPS * 32) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < LR_WARPS; ++w) sum += red[w][c];   // warp order: deterministic
+        float r = alpha * sum;
+        float* dst = C + row * ldc + c0 + c;
+        if (beta != 0.f) r = fmaf(beta, *dst, r);
+        *dst = r;
+      }
+    }
+  }
+
+  // ---- rows split over every warp of the grid: all blocks walk the list together
+  for (uint32_t i = 0; i < n_long; ++i) {
+    const int64_t row = lr.long_list[i];
+    const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+    for (int64_t c0 = 0; c0 < k; c0 += CW) {
+      float4 acc[KV];
+      row_segments<KV>(beg, end, (int64_t)blockIdx.x * LR_WARPS + warp, (int64_t)G * LR_WARPS, c0, k, vals, idx, B, ldb, acc);
+      __syncthreads();
+      stash(acc);
+      __syncthreads();
+      float* mine = partial_ws + (size_t)blockIdx.x * CW;
+      for (int c = threadIdx.x; c < CW; c += LR_WARPS * 32) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < LR_WARPS; ++w) sum += red[w][c];
+        mine[c] = sum;
+      }
+      grid_barrier(&lr.counters[2], &lr.counters[3], G);
+      if (blockIdx.x == i % G) {
+        for (int c = threadIdx.x; c < CW && c0 + c < k; c += LR_WARPS * 32) {
+          float sum = 0.f;
+          for (unsigned b = 0; b < G; ++b) sum += __ldcg(partial_ws + (size_t)b * CW + c);   // block order: deterministic
+          float r = alpha * sum;
+          float* dst = C + row * ldc + c0 + c;
+          if (beta != 0.f) r = fmaf(beta, *dst, r);
+          *dst = r;
+        }
+      }
+      grid_barrier(&lr.counters[2], &lr.counters[3], G);   // partial_ws may be overwritten again
+    }
+  }
+  // the last block out leaves the counters zeroed for the next launch (an empty launch never touches them)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&lr.counters[5], 1u) == G - 1) {
+      for (int i = 0; i < 8; ++i) lr.counters[i] = 0;
+    }
+  }
+}
+
 // Any k, any alignment: a warp owns a row and strides over the columns.
 __global__ void __launch_bounds__(256)
 spmm_csr_rm_generic_kernel(int64_t m, int64_t k, float alpha, const float* __restrict__ vals,
@@ -426,6 +630,17 @@ int spmm_tma_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float al
   return BOF_OK;
 }
 
+constexpr int kSlotSpmmLong = 36;   // context slot: counters, deferred-row lists, grid-path partials
+
+template <int KV>
+int long_rows_launch(bof_ctx* ctx, cudaStream_t s, int grid, int64_t k, float alpha, const float* vals, const int32_t* idx,
+                     const int64_t* offs, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                     const LongRows& lr, float* partial_ws) {
+  spmm_long_rows_kernel<KV><<<grid, LR_WARPS * 32, 0, s>>>(k, alpha, vals, idx, offs, B, ldb, beta, C, ldc, lr, partial_ws);
+  BOF_LAUNCH_CHECK(ctx, "spmm_long_rows_kernel");
+  return BOF_OK;
+}
+
 template <int L, int KV, int U = 4, int MINB = 4>
 int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                     const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
@@ -433,9 +648,47 @@ int spmm_vec_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float al
   constexpr int ROWS_PER_BLOCK = 8 * (32 / L);
   dim3 grid((unsigned)ceil_div<int64_t>(m, ROWS_PER_BLOCK),
             (unsigned)ceil_div<int64_t>(k, 4 * L * KV));
+  // state of the deferred-row path: [counters 256 B | long_list | partials G x 512 floats | mid_list m entries]
+  static const bool defer = getenv("BOF_SPMM_NO_SPLIT") == nullptr;
+  LongRows lr{nullptr, nullptr, nullptr};
+  float* partial_ws = nullptr;
+  int lgrid = 0;
+  if (defer && m < (1ll << 31)) {
+    const int kv = k <= 128 ? 1 : (k <= 256 ? 2 : 4);
+    static int occ[3] = {-1, -1, -1};   // blocks per SM of the three instantiations (same for every B200)
+    int& per_sm = occ[kv == 1 ? 0 : (kv == 2 ? 1 : 2)];
+    cudaError_t oe = cudaSuccess;
+    if (per_sm < 0)
+      oe = kv == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_long_rows_kernel<1>, LR_WARPS * 32, 0)
+         : kv == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_long_rows_kernel<2>, LR_WARPS * 32, 0)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmm_long_rows_kernel<4>, LR_WARPS * 32, 0);
+    if (oe == cudaSuccess && per_sm > 0) {
+      lgrid = ctx->num_sms * std::min(per_sm, 4);   // co-resident by construction: the grid barrier relies on it
+      size_t m_cap = 1024;
+      while ((int64_t)m_cap < m) m_cap <<= 1;       // power-of-two sizing: a streamed pipeline regrows the slot rarely
+      const size_t bytes = 256 + (size_t)kLongCap * 4 + (size_t)lgrid * 512 * 4 + m_cap * 4;
+      void* p = nullptr;
+      const size_t had = ctx->slot_bytes[kSlotSpmmLong];
+      { const int rc_slot = slot_reserve(ctx, kSlotSpmmLong, bytes, &p); if (rc_slot != BOF_OK) return rc_slot; }
+      // fresh memory: the counters start at zero; afterwards the long-row kernel leaves them zeroed itself
+      if (ctx->slot_bytes[kSlotSpmmLong] != had) BOF_CUDA(ctx, cudaMemsetAsync(p, 0, 256, s));
+      uint8_t* b8 = static_cast<uint8_t*>(p);
+      lr.counters = reinterpret_cast<uint32_t*>(b8);
+      lr.long_list = reinterpret_cast<int32_t*>(b8 + 256);
+      partial_ws = reinterpret_cast<float*>(b8 + 256 + (size_t)kLongCap * 4);
+      lr.mid_list = reinterpret_cast<int32_t*>(b8 + 256 + (size_t)kLongCap * 4 + (size_t)lgrid * 512 * 4);
+    } else {
+      cudaGetLastError();
+    }
+  }
   spmm_csr_rm_vec_kernel<L, KV, U, MINB><<<grid, 256, 0, s>>>(m, k, alpha, vals, idx, offs, B, ldb, beta,
-                                                              C, ldc);
+                                                              C, ldc, lr);
   BOF_LAUNCH_CHECK(ctx, "spmm_csr_rm_vec_kernel");
+  if (lr.counters != nullptr) {
+    if (k <= 128) return long_rows_launch<1>(ctx, s, lgrid, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc, lr, partial_ws);
+    if (k <= 256) return long_rows_launch<2>(ctx, s, lgrid, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc, lr, partial_ws);
+    return long_rows_launch<4>(ctx, s, lgrid, k, alpha, vals, idx, offs, B, ldb, beta, C, ldc, lr, partial_ws);
+  }
   return BOF_OK;
 }
 

@@ -209,3 +209,59 @@ def test_spmm_l2_half_policy_shape(ctx, k):
     ctx.spmm("R", m, n, k, 1.5, vals, idx, offs, dev(B), k, 0.5, Cd, k)
     ref = oracle.csrmm("N", m, n, k, 1.5, 0.5, a, ia, ja, "R", B, C0, acc64=True)
     assert oracle.rel_fro(Cd.cpu().numpy(), ref) <= TOL
+
+
+def zipf_csr(rng, m, n, nnz_target, max_row=None):
+    """power-law row lengths: row of rank r gets ~ nnz_target / (r * H_m) nonzeros (capped at n), in random row order"""
+    ranks = rng.permutation(m) + 1
+    lens = np.minimum((nnz_target / (ranks * np.log(m))).astype(np.int64) + 1, max_row or n)
+    ia = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ja = np.empty(int(ia[-1]), np.int64)
+    for r in range(m):
+        L = int(lens[r])
+        ja[ia[r]:ia[r + 1]] = np.sort(rng.choice(n, size=L, replace=False)) if L < n // 4 else np.sort(rng.permutation(n)[:L])
+    a = rng.random(int(ia[-1]), dtype=np.float32)
+    return a, ia, ja
+
+
+@pytest.mark.parametrize("k", [32, 128, 256, 640])
+def test_spmm_power_law_rows(ctx, k):
+    """row splitting: rows above 1024 nonzeros go to the 8 warps of a block, rows above max(16384, 64 x mean) to every
+    warp of the grid (deterministic combine); checked against the oracle on a Zipf row-length distribution"""
+    rng = np.random.default_rng(100 + k)
+    m, n = 6000, 40000
+    a, ia, ja = zipf_csr(rng, m, n, 1_200_000)
+    lens = np.diff(ia)
+    assert lens.max() > 20000 and (lens > 1024).sum() > 10 and np.median(lens) < 100
+    B = rng.random((n, k), dtype=np.float32)
+    C0 = rng.random((m, k), dtype=np.float32)
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+        Cd = dev(C0 if beta else np.full((m, k), np.nan, np.float32))
+        ctx.spmm("R", m, n, k, alpha, vals, idx, offs, dev(B), k, beta, Cd, k)
+        got = Cd.cpu().numpy()
+        ref = oracle.csrmm("N", m, n, k, alpha, beta, a, ia, ja, "R", B, C0, acc64=True)
+        assert oracle.rel_fro(got, ref) <= TOL
+        # per-row check of the longest rows (a global Frobenius norm would hide one bad row)
+        for r in np.argsort(lens)[-4:]:
+            assert oracle.rel_fro(got[r], ref[r]) <= TOL
+        Cd2 = dev(C0 if beta else np.full((m, k), np.nan, np.float32))
+        ctx.spmm("R", m, n, k, alpha, vals, idx, offs, dev(B), k, beta, Cd2, k)
+        assert torch.equal(Cd, Cd2)   # deterministic
+
+
+def test_spmm_poisoned_unused_rows_of_b(ctx):
+    """rows of B that no nonzero references may hold Inf / NaN: nothing of them may leak into C (long-row path too)"""
+    rng = np.random.default_rng(7)
+    m, n, k = 300, 9000, 128
+    lens = np.full(m, 8); lens[5] = 3000; lens[77] = 1500
+    ia = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ja = np.concatenate([np.sort(rng.choice(np.arange(1, n), size=L, replace=False)) for L in lens]).astype(np.int64)
+    a = rng.random(ja.size, dtype=np.float32)
+    B = rng.random((n, k), dtype=np.float32)
+    B[0] = np.inf   # column 0 is never referenced
+    vals, idx, offs = csr_to_device(a, ia, ja)
+    Cd = dev(np.zeros((m, k), np.float32))
+    ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, dev(B), k, 0.0, Cd, k)
+    Bz = B.copy(); Bz[0] = 0
+    assert oracle.rel_fro(Cd.cpu().numpy(), oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", Bz, np.zeros((m, k), np.float32), acc64=True)) <= TOL
