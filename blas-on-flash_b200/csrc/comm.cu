@@ -25,6 +25,7 @@ struct NcclApi {
   void* handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;   // optional
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -56,6 +57,7 @@ static const NcclApi* nccl_api() {
     g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
     g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+    g_nccl.CommInitRankConfig = reinterpret_cast<decltype(g_nccl.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
     if (!ok) g_nccl.handle = nullptr;
   });
   return g_nccl.handle ? &g_nccl : nullptr;
@@ -64,7 +66,16 @@ static const NcclApi* nccl_api() {
 struct CommState {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  int max_ctas = 0;   // CTAs an NCCL kernel of this communicator may occupy (0: unknown / unlimited)
 };
+
+// CTAs per collective kernel: few, because the panel broadcasts run next to persistent tensor-core kernels and only
+// have to keep up with PCIe-rate uploads of the other ranks (BOF_NCCL_MAX_CTAS overrides)
+static int nccl_max_ctas() {
+  const char* e = getenv("BOF_NCCL_MAX_CTAS");
+  const int v = e ? atoi(e) : 8;
+  return std::min(32, std::max(1, v));
+}
 
 #define BOF_NCCL(ctx, expr)                                                                              \
   do {                                                                                                   \
@@ -74,6 +85,11 @@ struct CommState {
   } while (0)
 
 int comm_world(const bof_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->world : 1; }
+// SMs to keep free for collective kernels that may be waiting on the GPU (pairs of SMs: the GEMM launches 2-CTA clusters)
+int comm_sm_reserve(const bof_ctx* ctx) {
+  if (!ctx || !ctx->comm || ctx->comm->world <= 1) return 0;
+  return 2 * (ctx->comm->max_ctas > 0 ? ctx->comm->max_ctas : 16);
+}
 int comm_rank(const bof_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }
 
 // Broadcast `count` floats at `buf` (same address role on every rank) from `root`, on the context's collective
@@ -127,7 +143,17 @@ int bof_comm_init(bof_ctx* ctx, int world, int rank, const void* id) {
   memcpy(&uid, id, sizeof(uid));
   CommState* cs = new CommState();
   cs->world = world; cs->rank = rank;
-  ncclResult_t r = api->CommInitRank(&cs->comm, world, uid, rank);
+  ncclResult_t r;
+  if (api->CommInitRankConfig != nullptr) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.maxCTAs = nccl_max_ctas();
+    cfg.minCTAs = 1;
+    cfg.cgaClusterSize = 1;   // no CTA clusters: the CTAs must fit into whatever SMs are free
+    r = api->CommInitRankConfig(&cs->comm, world, uid, rank, &cfg);
+    cs->max_ctas = cfg.maxCTAs;
+  } else {
+    r = api->CommInitRank(&cs->comm, world, uid, rank);
+  }
   if (r != ncclSuccess) {
     delete cs;
     return fail(ctx, BOF_ECUDA, "ncclCommInitRank failed: %s", api->GetErrorString(r));

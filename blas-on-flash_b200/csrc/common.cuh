@@ -77,6 +77,10 @@ struct bof_ctx {
   // multi-GPU: communicator of this context's rank (comm.cu), collectives run on `coll`
   bof::CommState* comm = nullptr;
   cudaStream_t coll = nullptr;
+  // SMs the persistent tensor-core kernels leave free while collectives of the same call may be waiting on the GPU:
+  // an NCCL kernel that waits for a peer holds its CTAs, and a persistent grid that needs every SM would wait for it
+  // (seen with BOF_TRACE at 2 GPUs: 20 ms stalls of the MMAs behind a broadcast whose root had not uploaded yet)
+  int sm_reserve = 0;
 };
 
 namespace bof {

@@ -332,9 +332,13 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // Uploads and launches are issued panel by panel: with pinned memory the order of issue is immaterial (everything
   // is asynchronous), but a pageable upload blocks this thread while it is staged, and launching only after the
   // whole prologue had been uploaded left the GPU idle for the first 170 ms at 32768^3 (BOF_TRACE).
+  // launches issued before the last panel has been waited for may run while a broadcast of a later panel is still
+  // waiting on this GPU for its root: leave it its SMs (see bof_ctx::sm_reserve).  The guard restores 0 on any exit.
+  struct ReserveGuard { bof_ctx* c; ~ReserveGuard() { c->sm_reserve = 0; } } reserve_guard{ctx};
   for (int t = 0; t < n_qpan; ++t) {
     int64_t n0, n1;
     pan(t, &n0, &n1);
+    ctx->sm_reserve = (dist && t < n_qpan - 1) ? comm_sm_reserve(ctx) : 0;
     BOF_TRY(upload_q_panel(t));
     if (t < npro) BOF_TRY(upload_block(t));
     BOF_TRY(split_q_panel(t));

@@ -750,7 +750,7 @@ int launch_variant(bof_ctx* ctx, cudaStream_t s, const CUtensorMap* maps, const 
     BOF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     attr_set.done(ctx->device);
   }
-  const int max_clusters = ctx->num_sms / CG;
+  const int max_clusters = std::max(1, (ctx->num_sms - ctx->sm_reserve) / CG);
   const int clusters = std::max(1, std::min(num_items, max_clusters));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
@@ -839,7 +839,7 @@ int launch_gemm_tc(bof_ctx* ctx, cudaStream_t s, int cta_group, int64_t M, int64
   const bool chunked = prm.kb_per_chunk < prm.num_kb;
   const int num_items = argmin ? prm.tiles_m : prm.tiles_m * prm.tiles_n;
   // wave lock-step only pays when a tile's k-panel outgrows L2 and there is more than one wave
-  const int clusters = std::max(1, std::min(num_items, ctx->num_sms / cta_group));
+  const int clusters = std::max(1, std::min(num_items, std::max(1, (ctx->num_sms - ctx->sm_reserve) / cta_group)));
   prm.sync_kb = 0;
   prm.sync_counters = nullptr;
   if (!argmin && ctx->cfg.gemm_wave_sync >= 0 && prm.num_kb >= 256 && num_items > clusters) {

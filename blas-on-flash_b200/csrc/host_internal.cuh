@@ -86,6 +86,7 @@ int gemm_canon_device(bof_ctx* ctx, cudaStream_t s, const Canon& c, float alpha,
 // ---- comm.cu: communicator rank of a context (world 1 / rank 0 without one) ----
 int comm_world(const bof_ctx* ctx);
 int comm_rank(const bof_ctx* ctx);
+int comm_sm_reserve(const bof_ctx* ctx);
 int comm_broadcast_f32(bof_ctx* ctx, float* buf, size_t count, int root);            // on ctx->coll
 int comm_allreduce_sum_f32(bof_ctx* ctx, float* buf, size_t count, cudaStream_t s);
 void comm_destroy(bof_ctx* ctx);
