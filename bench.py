@@ -328,6 +328,10 @@ def run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local):
                 bound_ms = e["h2d_bytes_per_step"] / h2d / 1e6
                 e["pcie_h2d_bound_ms"] = bound_ms
                 e["x_of_pcie_bound"] = e["ms"] / bound_ms
+                both = extra["pcie"].get("both_gbs_per_gpu")
+                if both:  # both directions busy at once: the host moves (h2d + d2h) bytes at the measured duplex rate
+                    e["pcie_duplex_bound_ms"] = (e["h2d_bytes_per_step"] + e.get("d2h_bytes_per_step", 0)) / both / 1e6
+                    e["x_of_pcie_duplex_bound"] = e["ms"] / e["pcie_duplex_bound_ms"]
     return extra
 
 
@@ -463,8 +467,8 @@ def main():
             ctx.host_gemm("R", "N", "N", Mr, Ng, Kg, 1.0, 0.0, Ah, Bh, Ch)  # returns after the D2H completed
             st_ = ctx.stats()
             return st_.h2d_bytes, st_.d2h_bytes
-        # N > 1: B is replicated.  bof_dist_gemm: panel j of B is uploaded by rank j % N only and broadcast over
-        # NVLink on the library's collective stream while the tensor cores work on the panels that have arrived;
+        # N > 1: B is replicated.  bof_dist_gemm: panel j of B is uploaded by rank j % N only and pushed into every
+        # peer's HBM by copy-engine peer copies over NVLink while the tensor cores work on the panels that have arrived;
         # only the A shard, 1/N of B and the C shard cross this GPU's PCIe link.
         ctx.dist_gemm("N", "N", Mr, Ng, Kg, 1.0, 0.0, Ah, Bh, Ch)
         st_ = ctx.stats()
@@ -484,8 +488,8 @@ def main():
            "d2h_bytes_per_step": d2h_b, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
            "pcie_gbs": (h2d_b + d2h_b) / t_e2e / 1e9,
            "api": "bof_host_gemm (C ABI behind flash::gemm), pinned host A/B/C" if world == 1 else
-                  "bof_dist_gemm (C ABI): per rank 1/N of B's column panels H2D + NCCL panel broadcasts over NVLink overlapped with "
-                  "the MMAs, C downloaded slab by slab; pinned host A/B/C"}
+                  "bof_dist_gemm (C ABI): per rank 1/N of B's column panels H2D, pushed to the peers' HBM by copy-engine peer copies "
+                  "over NVLink (arrival flags, no SMs) overlapped with the MMAs, C downloaded slab by slab; pinned host A/B/C"}
     i0 = int(torch.randint(0, Mr, (1,))); j0 = int(torch.randint(0, Ng, (1,)))
     ref0 = float((Ah[i0].double() * Bh[:, j0].double()).sum())
     e2e["spot_rel_err"] = abs(float(Ch[i0, j0]) - ref0) / abs(ref0)
@@ -498,6 +502,15 @@ def main():
         extra = run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local)
     launches_extra = ctx.launch_count() - l2
 
+    if "pcie" in extra and extra["pcie"].get("h2d_gbs_per_gpu"):
+        pc = extra["pcie"]
+        e2e["pcie_h2d_bound_ms"] = h2d_b / pc["h2d_gbs_per_gpu"] / 1e6
+        e2e["pcie_duplex_bound_ms"] = (h2d_b + d2h_b) / pc["both_gbs_per_gpu"] / 1e6
+        e2e["kernel_ms"] = t_kernel * 1e3
+        e2e["x_of_bound"] = e2e["ms_per_step"] / max(e2e["pcie_h2d_bound_ms"], e2e["kernel_ms"])
+        e2e["x_of_duplex_bound"] = e2e["ms_per_step"] / max(e2e["pcie_duplex_bound_ms"], e2e["kernel_ms"])
+        e2e["bound_note"] = ("per-GPU bytes of this run / pinned-copy rates measured in this run with all ranks copying at once "
+                             "(extra.pcie): H2D alone, and H2D + D2H at the both-directions rate")
     if rank == 0:
         line = {
             "metric": "gemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,

@@ -5,6 +5,14 @@
 // broadcasts panel by panel so that it crosses PCIe once per node instead of once per GPU, and
 // (ii) the k-means allreduce of centroid sums and counts, the only reduction on the path.
 //
+// The replicated operand does NOT travel through NCCL kernels: an NCCL kernel that waits for its root holds SMs, and
+// next to a persistent tensor-core grid that stalls the MMAs (measured, profiles/r02).  Instead every rank owns an
+// EXCHANGE BUFFER in HBM that its peers map (CUDA IPC between processes, plain peer pointers inside one process), and
+// the owner of a panel pushes it into every peer's buffer with copy-engine peer copies over NVLink / NVSwitch,
+// followed by a 32-bit flag write (cuStreamWriteValue32); consumers gate their streams with cuStreamWaitValue32.
+// No SM is involved, no host thread waits, and nothing crosses a process boundary except device memory.
+// NCCL keeps two jobs: the bootstrap all-gather of the IPC handles and the k-means allreduce.
+//
 // NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the process already holds -- torch's, under
 // torchrun -- or the system one), so libbof_b200.so has no link-time dependency on it and single-GPU users never
 // load it.  Two ways to get ranks:
@@ -14,8 +22,10 @@
 //     worker thread per device and initialises the ranks itself.
 #include "host_internal.cuh"
 
+#include <cuda.h>
 #include <dlfcn.h>
-#include <nccl.h>   // types and enums only; every entry point is looked up with dlsym
+#include <nccl.h>
+#include <unistd.h>   // types and enums only; every entry point is looked up with dlsym
 
 #include <mutex>
 
@@ -63,10 +73,47 @@ static const NcclApi* nccl_api() {
   return g_nccl.handle ? &g_nccl : nullptr;
 }
 
+constexpr int kPushStreams = 4;
+constexpr int kFlagReady = 0;      // flags[kFlagReady + r]: rank r has finished its previous collective call
+constexpr int kFlagData = 64;      // flags[kFlagData + i]: item i of the current call has been pushed into my buffer
+constexpr int kFlagCount = 64 + 256;
+
+// what every rank publishes about itself (all-gathered through NCCL)
+struct PeerInfo {
+  uint64_t pid;
+  uint64_t epoch;            // bumps when the exchange buffer is reallocated
+  uint64_t xbuf_ptr;         // same-process peers use the pointers directly
+  uint64_t flags_ptr;
+  uint64_t xbuf_bytes;
+  int32_t device;
+  int32_t pad;
+  cudaIpcMemHandle_t xbuf_handle;
+  cudaIpcMemHandle_t flags_handle;
+};
+
+struct Peer {
+  int device = -1;
+  uint64_t epoch = ~0ull;     // epoch of the mapping we hold
+  float* xbuf = nullptr;
+  uint32_t* flags = nullptr;
+  bool xbuf_ipc = false, flags_ipc = false;
+};
+
 struct CommState {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
   int max_ctas = 0;   // CTAs an NCCL kernel of this communicator may occupy (0: unknown / unlimited)
+  // peer exchange
+  float* xbuf = nullptr;       // my exchange buffer (cudaMalloc: IPC-exportable)
+  size_t xbuf_bytes = 0;
+  uint64_t epoch = 0;
+  uint32_t* flags = nullptr;   // kFlagCount words, zero-initialised
+  uint32_t seq = 0;            // collective call counter (identical on every rank)
+  std::vector<Peer> peers;
+  cudaStream_t push[kPushStreams] = {};
+  PeerInfo* gather_dev = nullptr;   // world entries, for the bootstrap all-gather
+  uint32_t* seq_dev = nullptr;      // device copy of `seq`: source of the 4-byte flag writes into the peers
+  CUresult (*WaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
 };
 
 // CTAs per collective kernel: few, because the panel broadcasts run next to persistent tensor-core kernels and only
@@ -85,11 +132,6 @@ static int nccl_max_ctas() {
   } while (0)
 
 int comm_world(const bof_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->world : 1; }
-// SMs to keep free for collective kernels that may be waiting on the GPU (pairs of SMs: the GEMM launches 2-CTA clusters)
-int comm_sm_reserve(const bof_ctx* ctx) {
-  if (!ctx || !ctx->comm || ctx->comm->world <= 1) return 0;
-  return 2 * (ctx->comm->max_ctas > 0 ? ctx->comm->max_ctas : 16);
-}
 int comm_rank(const bof_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }
 
 // Broadcast `count` floats at `buf` (same address role on every rank) from `root`, on the context's collective
@@ -107,8 +149,146 @@ int comm_allreduce_sum_f32(bof_ctx* ctx, float* buf, size_t count, cudaStream_t 
   return BOF_OK;
 }
 
+// ---- peer exchange ------------------------------------------------------------------------------------------------
+
+static int publish_and_map(bof_ctx* ctx) {
+  CommState* cs = ctx->comm;
+  PeerInfo mine{};
+  mine.pid = (uint64_t)getpid();
+  mine.epoch = cs->epoch;
+  mine.xbuf_ptr = (uint64_t)(uintptr_t)cs->xbuf;
+  mine.flags_ptr = (uint64_t)(uintptr_t)cs->flags;
+  mine.xbuf_bytes = cs->xbuf_bytes;
+  mine.device = ctx->device;
+  if (cs->xbuf) BOF_CUDA(ctx, cudaIpcGetMemHandle(&mine.xbuf_handle, cs->xbuf));
+  BOF_CUDA(ctx, cudaIpcGetMemHandle(&mine.flags_handle, cs->flags));
+  BOF_CUDA(ctx, cudaMemcpyAsync(cs->gather_dev + cs->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->coll));
+  BOF_NCCL(ctx, g_nccl.AllGather(cs->gather_dev + cs->rank, cs->gather_dev, sizeof(PeerInfo), ncclInt8, cs->comm, ctx->coll));
+  std::vector<PeerInfo> all((size_t)cs->world);
+  BOF_CUDA(ctx, cudaMemcpyAsync(all.data(), cs->gather_dev, sizeof(PeerInfo) * cs->world, cudaMemcpyDeviceToHost, ctx->coll));
+  BOF_CUDA(ctx, cudaStreamSynchronize(ctx->coll));
+  for (int r = 0; r < cs->world; ++r) {
+    if (r == cs->rank) continue;
+    Peer& pr = cs->peers[r];
+    const PeerInfo& pi = all[r];
+    const bool same_process = pi.pid == mine.pid;
+    if (pr.device != pi.device) {
+      pr.device = pi.device;
+      if (pi.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(ctx, BOF_ECUDA, "no peer access from device %d to device %d: %s", ctx->device, pi.device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    }
+    if (pr.flags == nullptr) {
+      if (same_process) pr.flags = reinterpret_cast<uint32_t*>((uintptr_t)pi.flags_ptr);
+      else {
+        void* q = nullptr;
+        BOF_CUDA(ctx, cudaIpcOpenMemHandle(&q, pi.flags_handle, cudaIpcMemLazyEnablePeerAccess));
+        pr.flags = static_cast<uint32_t*>(q);
+        pr.flags_ipc = true;
+      }
+    }
+    if (pr.epoch != pi.epoch) {
+      if (pr.xbuf && pr.xbuf_ipc) BOF_CUDA(ctx, cudaIpcCloseMemHandle(pr.xbuf));
+      pr.xbuf = nullptr; pr.xbuf_ipc = false;
+      if (pi.xbuf_ptr != 0) {
+        if (same_process) pr.xbuf = reinterpret_cast<float*>((uintptr_t)pi.xbuf_ptr);
+        else {
+          void* q = nullptr;
+          BOF_CUDA(ctx, cudaIpcOpenMemHandle(&q, pi.xbuf_handle, cudaIpcMemLazyEnablePeerAccess));
+          pr.xbuf = static_cast<float*>(q);
+          pr.xbuf_ipc = true;
+        }
+      }
+      pr.epoch = pi.epoch;
+    }
+  }
+  return BOF_OK;
+}
+
+// Start of a collective call that exchanges up to `bytes` through the exchange buffers: grows mine if needed,
+// refreshes the peer mappings, and tells every peer that my buffer is free again (my previous call has returned).
+// Returns my exchange buffer.
+int comm_exchange_begin(bof_ctx* ctx, size_t bytes, float** xbuf_out) {
+  CommState* cs = ctx->comm;
+  if (!cs || cs->world <= 1) return fail(ctx, BOF_EINVAL, "peer exchange needs a communicator with more than one rank");
+  if (!cs->WaitValue32) return fail(ctx, BOF_ENODEV, "stream memory operations (cuStreamWaitValue32) are not available");
+  if (cs->xbuf_bytes < bytes) {
+    // every rank sees the same sizes (collective call), so every rank regrows in the same call
+    BOF_CUDA(ctx, cudaDeviceSynchronize());
+    if (cs->xbuf) BOF_CUDA(ctx, cudaFree(cs->xbuf));
+    cs->xbuf = nullptr; cs->xbuf_bytes = 0;
+    const size_t want = (bytes + ((size_t)64 << 20)) & ~(((size_t)2 << 20) - 1);
+    void* q = nullptr;
+    if (cudaMalloc(&q, want) != cudaSuccess) { cudaGetLastError(); return fail(ctx, BOF_ENOMEM, "exchange buffer: cudaMalloc of %zu bytes failed", want); }
+    cs->xbuf = static_cast<float*>(q);
+    cs->xbuf_bytes = want;
+    cs->epoch++;
+  }
+  // Peers may have regrown too; the all-gather also orders "every rank has entered call seq+1" after "every rank has
+  // left call seq" for the host side.  ~60 us per call.
+  BOF_TRY(publish_and_map(ctx));
+  cs->seq++;
+  // flags are raised with 4-byte peer copies of this word (in stream order behind the data they announce)
+  BOF_CUDA(ctx, cudaMemcpyAsync(cs->seq_dev, &cs->seq, sizeof(uint32_t), cudaMemcpyHostToDevice, cs->push[0]));
+  for (int r = 0; r < cs->world; ++r) {
+    if (r == cs->rank) continue;
+    BOF_CUDA(ctx, cudaMemcpyPeerAsync(cs->peers[r].flags + kFlagReady + cs->rank, cs->peers[r].device, cs->seq_dev, ctx->device,
+                                      sizeof(uint32_t), cs->push[0]));
+  }
+  cudaEvent_t ev = get_event(ctx, 120);
+  BOF_CUDA(ctx, cudaEventRecord(ev, cs->push[0]));
+  for (int i = 1; i < kPushStreams; ++i) BOF_CUDA(ctx, cudaStreamWaitEvent(cs->push[i], ev, 0));
+  *xbuf_out = cs->xbuf;
+  return BOF_OK;
+}
+
+// Push [offset, offset + count) floats of my exchange buffer into the same place of every peer's, after `ready` (an
+// event of this device, e.g. "my upload landed"), then raise data flag `item` there.
+int comm_push(bof_ctx* ctx, size_t offset, size_t count, int item, cudaEvent_t ready) {
+  CommState* cs = ctx->comm;
+  for (int d = 1; d < cs->world; ++d) {
+    const int r = (cs->rank + d) % cs->world;      // every owner starts with a different peer
+    cudaStream_t st = cs->push[r % kPushStreams];
+    Peer& pr = cs->peers[r];
+    if (ready) BOF_CUDA(ctx, cudaStreamWaitEvent(st, ready, 0));
+    // the peer's buffer is free once the peer has entered this call
+    if (cs->WaitValue32(st, (CUdeviceptr)(uintptr_t)(cs->flags + kFlagReady + r), cs->seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+      return fail(ctx, BOF_ECUDA, "cuStreamWaitValue32 failed");
+    BOF_CUDA(ctx, cudaMemcpyPeerAsync(pr.xbuf + offset, pr.device, cs->xbuf + offset, ctx->device, count * sizeof(float), st));
+    BOF_CUDA(ctx, cudaMemcpyPeerAsync(pr.flags + kFlagData + item, pr.device, cs->seq_dev, ctx->device, sizeof(uint32_t), st));
+  }
+  return BOF_OK;
+}
+
+// Make stream `s` wait until item `item` of the current call has arrived in my exchange buffer.
+int comm_wait_item(bof_ctx* ctx, cudaStream_t s, int item) {
+  CommState* cs = ctx->comm;
+  if (cs->WaitValue32(s, (CUdeviceptr)(uintptr_t)(cs->flags + kFlagData + item), cs->seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+    return fail(ctx, BOF_ECUDA, "cuStreamWaitValue32 failed");
+  return BOF_OK;
+}
+
+// All my pushes have left (my exchange buffer may be reused); part of sync_all.
+void comm_sync_pushes(bof_ctx* ctx) {
+  if (!ctx->comm) return;
+  for (int i = 0; i < kPushStreams; ++i)
+    if (ctx->comm->push[i]) cudaStreamSynchronize(ctx->comm->push[i]);
+}
+
 void comm_destroy(bof_ctx* ctx) {
   if (!ctx || !ctx->comm) return;
+  for (auto& pr : ctx->comm->peers) {
+    if (pr.xbuf && pr.xbuf_ipc) cudaIpcCloseMemHandle(pr.xbuf);
+    if (pr.flags && pr.flags_ipc) cudaIpcCloseMemHandle(pr.flags);
+  }
+  for (int i = 0; i < kPushStreams; ++i) if (ctx->comm->push[i]) cudaStreamDestroy(ctx->comm->push[i]);
+  if (ctx->comm->xbuf) cudaFree(ctx->comm->xbuf);
+  if (ctx->comm->flags) cudaFree(ctx->comm->flags);
+  if (ctx->comm->gather_dev) cudaFree(ctx->comm->gather_dev);
+  if (ctx->comm->seq_dev) cudaFree(ctx->comm->seq_dev);
   if (ctx->comm->comm && g_nccl.handle) g_nccl.CommDestroy(ctx->comm->comm);
   delete ctx->comm;
   ctx->comm = nullptr;
@@ -160,6 +340,19 @@ int bof_comm_init(bof_ctx* ctx, int world, int rank, const void* id) {
   }
   ctx->comm = cs;
   BOF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->coll, cudaStreamNonBlocking));
+  // peer exchange state
+  cs->peers.resize((size_t)world);
+  for (int i = 0; i < kPushStreams; ++i) BOF_CUDA(ctx, cudaStreamCreateWithFlags(&cs->push[i], cudaStreamNonBlocking));
+  BOF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&cs->flags), kFlagCount * sizeof(uint32_t)));
+  BOF_CUDA(ctx, cudaMemset(cs->flags, 0, kFlagCount * sizeof(uint32_t)));
+  BOF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&cs->gather_dev), sizeof(PeerInfo) * world));
+  BOF_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&cs->seq_dev), 256));
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    cs->WaitValue32 = reinterpret_cast<decltype(cs->WaitValue32)>(fn);
+  if (!cs->WaitValue32) cudaGetLastError();
+  if (world > 1) BOF_TRY(publish_and_map(ctx));   // flags of every peer (no exchange buffer yet)
   return BOF_OK;
 }
 

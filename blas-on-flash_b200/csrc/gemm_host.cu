@@ -126,7 +126,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   float* qraw = nullptr;
   float* q_hi = nullptr;
   float* q_lo = nullptr;
+  const bool dist_mode = dist_q && comm_world(ctx) > 1 && tensor;   // Q lives in the exchange buffer the peers push into
   if (q_on_device) qraw = const_cast<float*>(cn.qsrc);  // B already in HBM in its source layout; read-only here
+  else if (dist_mode) BOF_TRY(comm_exchange_begin(ctx, (size_t)cn.No * std::max<int64_t>(K, 1) * sizeof(float), &qraw));
   else BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)cn.No * std::max<int64_t>(K, 1), &qraw));
   const size_t qb = plane_bytes(cn.No, kp);
   if (tensor) {
@@ -267,13 +269,13 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // j % world only and broadcast over NVLink on the collective stream, so Q crosses PCIe once per node; every
   // rank consumes the panels in the same order as they arrive, exactly like its own uploads.
   const int world = dist_q ? comm_world(ctx) : 1, rank = comm_rank(ctx);
-  const bool dist = dist_q && world > 1 && tensor;
+  const bool dist = dist_mode;
   const bool q_panels = tensor && !q_on_device && (dist || (size_t)cn.No * K * 4 >= (256u << 20));
   static const int64_t n_q_panels_env = getenv("BOF_GEMM_QPANELS") ? std::min(16, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 0;
   const int64_t n_q_panels = n_q_panels_env ? n_q_panels_env : (dist ? (world >= 8 ? 16 : 8) : 8);
   const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, n_q_panels), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
-  constexpr int EV_OWN = 64, EV_SLAB = 88;
+  constexpr int EV_SLAB = 88;
   // Every panel is kept as its own tight block at qraw + n0*K: [rows x K] when Q is K-major in the source,
   // [K x rows] (a column range of the stored matrix, pitched copy) when it is not.
   std::vector<int64_t> pan_sr((size_t)n_qpan, 1), pan_sk((size_t)n_qpan, 1);
@@ -283,14 +285,12 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
       const int owner = j % world;
       if (cn.q_sk == 1) { pan_sr[j] = K; pan_sk[j] = 1; } else { pan_sr[j] = 1; pan_sk[j] = n1 - n0; }  // what upload_rows produces
       if (owner == rank) {
+        // upload my panel, then push it into every peer's exchange buffer with copy-engine peer copies (no SMs)
         BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &pan_sr[j], &pan_sk[j], ctx->h2d));
-        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_OWN + j), ctx->h2d));
-        BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->coll, get_event(ctx, EV_OWN + j), 0));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->h2d));
         trace_mark(ctx, ctx->h2d, "h2d: own Q panel landed", j);
+        BOF_TRY(comm_push(ctx, (size_t)(n0 * K), (size_t)(n1 - n0) * K, j, get_event(ctx, EV_QPAN + j)));
       }
-      BOF_TRY(comm_broadcast_f32(ctx, qraw + n0 * K, (size_t)(n1 - n0) * K, owner));
-      BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_QPAN + j), ctx->coll));
-      trace_mark(ctx, ctx->coll, "coll: Q panel broadcast done", j);
       return BOF_OK;
     }
     if (q_on_device) { pan_sr[j] = cn.q_sr; pan_sk[j] = cn.q_sk; }  // single panel, source strides
@@ -302,7 +302,12 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   };
   auto split_q_panel = [&](int j) -> int {
     const int64_t n0 = (int64_t)j * qpan_rows, n1 = std::min(cn.No, n0 + qpan_rows);
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_QPAN + j), 0));
+    if (dist && j % world != rank) {
+      BOF_TRY(comm_wait_item(ctx, ctx->compute, j));   // pushed by its owner: gate on the arrival flag
+      trace_mark(ctx, ctx->compute, "compute: peer Q panel arrived", j);
+    } else {
+      BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, get_event(ctx, EV_QPAN + j), 0));
+    }
     if (!tensor) return BOF_OK;
     return launch_split_planes(ctx, ctx->compute, n1 - n0, K, qraw + n0 * K, pan_sr[j], pan_sk[j], q_hi + n0 * kp,
                                q_lo + n0 * kp, kp);
@@ -332,13 +337,9 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // Uploads and launches are issued panel by panel: with pinned memory the order of issue is immaterial (everything
   // is asynchronous), but a pageable upload blocks this thread while it is staged, and launching only after the
   // whole prologue had been uploaded left the GPU idle for the first 170 ms at 32768^3 (BOF_TRACE).
-  // launches issued before the last panel has been waited for may run while a broadcast of a later panel is still
-  // waiting on this GPU for its root: leave it its SMs (see bof_ctx::sm_reserve).  The guard restores 0 on any exit.
-  struct ReserveGuard { bof_ctx* c; ~ReserveGuard() { c->sm_reserve = 0; } } reserve_guard{ctx};
   for (int t = 0; t < n_qpan; ++t) {
     int64_t n0, n1;
     pan(t, &n0, &n1);
-    ctx->sm_reserve = (dist && t < n_qpan - 1) ? comm_sm_reserve(ctx) : 0;
     BOF_TRY(upload_q_panel(t));
     if (t < npro) BOF_TRY(upload_block(t));
     BOF_TRY(split_q_panel(t));

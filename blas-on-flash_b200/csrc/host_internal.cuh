@@ -86,10 +86,14 @@ int gemm_canon_device(bof_ctx* ctx, cudaStream_t s, const Canon& c, float alpha,
 // ---- comm.cu: communicator rank of a context (world 1 / rank 0 without one) ----
 int comm_world(const bof_ctx* ctx);
 int comm_rank(const bof_ctx* ctx);
-int comm_sm_reserve(const bof_ctx* ctx);
 int comm_broadcast_f32(bof_ctx* ctx, float* buf, size_t count, int root);            // on ctx->coll
 int comm_allreduce_sum_f32(bof_ctx* ctx, float* buf, size_t count, cudaStream_t s);
 void comm_destroy(bof_ctx* ctx);
+// peer exchange of the replicated operand (copy engines over NVLink + stream memory-op flags; comm.cu)
+int comm_exchange_begin(bof_ctx* ctx, size_t bytes, float** xbuf_out);
+int comm_push(bof_ctx* ctx, size_t offset, size_t count, int item, cudaEvent_t ready);
+int comm_wait_item(bof_ctx* ctx, cudaStream_t s, int item);
+void comm_sync_pushes(bof_ctx* ctx);
 
 // ---- sparse_host.cu ----
 std::vector<int64_t> partition_rows(const int64_t* ia, int64_t m, int64_t max_nnz);

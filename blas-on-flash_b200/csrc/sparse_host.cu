@@ -48,39 +48,55 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
 
   // resident dense operand, always row-major [in_rows x k] on the device
   float* Bd = nullptr;
+  const bool dist_mode = dist_b && comm_world(ctx) > 1;
   if (b_dev != nullptr) {
     Bd = const_cast<float*>(b_dev);  // already in HBM (e.g. all-gathered over NVLink); read-only here
+  } else if (dist_mode) {
+    BOF_TRY(comm_exchange_begin(ctx, (size_t)in_rows * k * sizeof(float), &Bd));   // the buffer the peers push into
   } else {
     BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)in_rows * k, &Bd));
   }
   const int world = dist_b ? comm_world(ctx) : 1, rank = comm_rank(ctx);
   if (b_dev != nullptr) {
     // nothing to upload
-  } else if (dist_b && world > 1) {
+  } else if (dist_mode) {
     // bof_dist_csrmm: B is replicated over the ranks.  Every rank uploads rows [r0, r1) of it (1/world of the PCIe
-    // traffic) and the slices are exchanged over NVLink on the collective stream; meanwhile this rank's first A
-    // blocks already upload behind the slice.  The SpMM gathers arbitrary rows of B, so it waits for all of it.
+    // traffic) in a few pieces and pushes each piece into every peer's exchange buffer with copy-engine peer copies
+    // over NVLink as soon as it has landed; meanwhile this rank's first A blocks upload behind the slice.  The SpMM
+    // gathers arbitrary rows of B, so the compute stream waits for every piece of every rank.
+    constexpr int kPieces = 4;
     auto shard = [&](int r, int64_t* r0, int64_t* r1) {
       const int64_t base = in_rows / world, rem = in_rows % world;
       *r0 = r * base + std::min<int64_t>(r, rem);
       *r1 = *r0 + base + (r < rem ? 1 : 0);
     };
-    int64_t r0, r1;
-    shard(rank, &r0, &r1);
-    BOF_TRY(copy1d(ctx, Bd + r0 * k, b + r0 * k, (size_t)(r1 - r0) * k * 4, H2D, ctx->h2d));
-    cudaEvent_t ev_own = get_event(ctx, 1);
-    BOF_CUDA(ctx, cudaEventRecord(ev_own, ctx->h2d));
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->coll, ev_own, 0));
+    auto piece = [&](int r, int q, int64_t* p0, int64_t* p1) {
+      int64_t r0, r1;
+      shard(r, &r0, &r1);
+      const int64_t per = ceil_div<int64_t>(r1 - r0, kPieces);
+      *p0 = std::min(r1, r0 + q * per);
+      *p1 = std::min(r1, *p0 + per);
+    };
+    for (int q = 0; q < kPieces; ++q) {
+      int64_t p0, p1;
+      piece(rank, q, &p0, &p1);
+      if (p1 <= p0) continue;
+      BOF_TRY(copy1d(ctx, Bd + p0 * k, b + p0 * k, (size_t)(p1 - p0) * k * 4, H2D, ctx->h2d));
+      cudaEvent_t ev_own = get_event(ctx, 100 + q);
+      BOF_CUDA(ctx, cudaEventRecord(ev_own, ctx->h2d));
+      BOF_TRY(comm_push(ctx, (size_t)(p0 * k), (size_t)(p1 - p0) * k, rank * kPieces + q, ev_own));
+      if (q == kPieces - 1) BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_own, 0));
+    }
     trace_mark(ctx, ctx->h2d, "h2d: own slice of the dense operand landed", rank);
     for (int src = 0; src < world; ++src) {
-      int64_t s0, s1;
-      shard(src, &s0, &s1);
-      if (s1 > s0) BOF_TRY(comm_broadcast_f32(ctx, Bd + s0 * k, (size_t)(s1 - s0) * k, src));
+      if (src == rank) continue;
+      for (int q = 0; q < kPieces; ++q) {
+        int64_t p0, p1;
+        piece(src, q, &p0, &p1);
+        if (p1 > p0) BOF_TRY(comm_wait_item(ctx, ctx->compute, src * kPieces + q));
+      }
     }
-    cudaEvent_t evB = get_event(ctx, 0);
-    BOF_CUDA(ctx, cudaEventRecord(evB, ctx->coll));
-    BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
-    trace_mark(ctx, ctx->coll, "coll: dense operand complete on this rank", 0);
+    trace_mark(ctx, ctx->compute, "compute: dense operand complete on this rank", 0);
   } else if (colmaj) {
     float* Braw = nullptr;
     BOF_TRY(slot_reserve(ctx, S_DENSE_T, (size_t)in_rows * k, &Braw));

@@ -513,6 +513,7 @@ int sync_all(bof_ctx* ctx) {
   if (ctx->drainer) ctx->drainer->wait_all_issued();  // the drainer may still be enqueueing copies on the streams
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
   if (ctx->coll) BOF_CUDA(ctx, cudaStreamSynchronize(ctx->coll));
+  comm_sync_pushes(ctx);
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
   BOF_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
   return drain_wait(ctx);
@@ -524,6 +525,7 @@ void quiesce(bof_ctx* ctx) {
   if (ctx->drainer) ctx->drainer->wait_all_issued();
   cudaStreamSynchronize(ctx->h2d);
   if (ctx->coll) cudaStreamSynchronize(ctx->coll);
+  comm_sync_pushes(ctx);
   cudaStreamSynchronize(ctx->compute);
   cudaStreamSynchronize(ctx->d2h);
   if (ctx->drainer) ctx->drainer->wait_idle();

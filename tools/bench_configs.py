@@ -241,8 +241,8 @@ def csrmm_cfg3(env: Env, scale=1.0):
                   "api": "bof_host_csrmm, pinned host buffers, B uploaded by every rank (replicated)"}
     par["rel_fro_sampled_rows_e2e"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
     if world > 1:
-        # SURVEY 8(f)-1 behind the C ABI: every rank uploads 1/N of B's rows, the slices are broadcast over NVLink on the
-        # library's collective stream while this rank's first A blocks upload, then the row-block pipeline runs
+        # SURVEY 8(f)-1 behind the C ABI: every rank uploads 1/N of B's rows and pushes them into every peer's exchange
+        # buffer (copy engines over NVLink) while this rank's first A blocks upload, then the row-block pipeline runs
         from bof_b200 import dist as bdist
         bdist.init_comm(ctx)
         C_h.zero_()
@@ -251,7 +251,7 @@ def csrmm_cfg3(env: Env, scale=1.0):
         rec["e2e_shared_b"] = {"value": 2.0 * nnz * k / tg / 1e9, "unit": "GFLOP/s", "ms": tg * 1e3,
                                "h2d_bytes_per_step": st.h2d_bytes, "d2h_bytes_per_step": st.d2h_bytes,
                                "h2d_gbs_per_gpu": st.h2d_bytes / tg / 1e9,
-                               "api": "bof_dist_csrmm: 1/N of B H2D per rank + NCCL broadcasts over NVLink, then the row-block pipeline"}
+                               "api": "bof_dist_csrmm: 1/N of B H2D per rank, pushed into every peer's HBM by copy-engine peer copies over NVLink, then the row-block pipeline"}
         par["rel_fro_sampled_rows_shared_b"] = float(np.linalg.norm(C_h[torch.from_numpy(rows)].numpy() - ref) / np.linalg.norm(ref))
     if env.cpu:
         try:
