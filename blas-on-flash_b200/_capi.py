@@ -29,6 +29,7 @@ class BofConfig(C.Structure):
         ("gemm_wave_sync", C.c_int32),
         ("gemm_split", C.c_int32),
         ("radix_max_bits", C.c_int32),
+        ("spmv_t_atomic", C.c_int32),
     ]
 
 

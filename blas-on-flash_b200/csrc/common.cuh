@@ -154,8 +154,16 @@ int slot_reserve(bof_ctx* ctx, int slot, size_t count, T** out) {
 int launch_spmm_rm(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float alpha,
                    const float* vals, const int32_t* idx, const int64_t* offs, const float* B,
                    int64_t ldb, float beta, float* C, int64_t ldc, int64_t b_rows = 0);
+// trans 'N'; 'T' (y zeroed first) / 't' (y += A^T x).  The transposed product is deterministic by default: products
+// sorted stably by column, fixed-order column sums (radix.cu); bof_config.spmv_t_atomic = 1 selects the scatter kernel
+// with red.global.add.f32 instead (faster, order of the additions varies from run to run).  nnz < 0: read from offs.
 int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
-                const int32_t* idx, const int64_t* offs, const float* x, float* y);
+                const int32_t* idx, const int64_t* offs, const float* x, float* y, int64_t nnz = -1);
+size_t spmv_t_workspace_bytes(int64_t n, int64_t nnz);
+int launch_spmv_t_sorted(bof_ctx* ctx, cudaStream_t s, int accumulate, int64_t m, int64_t n, int64_t nnz, const float* vals,
+                         const int32_t* idx, const int64_t* offs, const float* x, float* y, void* ws, size_t ws_bytes);
+constexpr int kSlotSpmvT = 35;      // context slot: workspace of the sorted A^T x path
+constexpr int kSlotSpmmLong = 36;   // context slot: counters, deferred-row lists, grid-path partials of the SpMM
 int launch_idx_narrow(bof_ctx* ctx, cudaStream_t s, const int64_t* in, int32_t* out, int64_t n);
 int launch_idx_widen(bof_ctx* ctx, cudaStream_t s, const int32_t* in, int64_t* out, int64_t n);
 // out[c * ldo + r] = in[r * ldi + c] for an rows x cols row-major input

@@ -392,6 +392,38 @@ __global__ void iota_kernel(uint32_t* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint32_t)i;
 }
 
+
+// ---- deterministic y = A^T x (K5) --------------------------------------------------------------------------------
+// prod[j] = vals[j] * x[row(j)], a warp per row
+__global__ void __launch_bounds__(256)
+row_products_kernel(int64_t m, const float* __restrict__ vals, const int64_t* __restrict__ offs,
+                    const float* __restrict__ x, uint32_t* __restrict__ prod) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const int64_t base = offs[0];
+  const int64_t beg = offs[row] - base, end = offs[row + 1] - base;
+  const float xr = __ldg(x + row);
+  for (int64_t j = beg + lane; j < end; j += 32) prod[j] = __float_as_uint(__ldcs(vals + j) * xr);
+}
+
+// y[c] (+)= sum of the products of column c in ascending source row: one lane group of 8 per column, the partial
+// sums of the 8 lanes combined in lane order -- a fixed summation tree, so the result is reproducible
+__global__ void __launch_bounds__(256)
+segment_sum_kernel(int64_t n, const int64_t* __restrict__ seg_offs, const uint32_t* __restrict__ prod,
+                   float* __restrict__ y, int accumulate) {
+  const int lane = threadIdx.x & 31, sl = lane & 7;
+  const int64_t c = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  float acc = 0.f;
+  if (c < n) {
+    const int64_t beg = seg_offs[c], end = seg_offs[c + 1];
+    for (int64_t j = beg + sl; j < end; j += 8) acc += __uint_as_float(__ldcs(prod + j));
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (c < n && sl == 0) y[c] = accumulate ? y[c] + acc : acc;
+}
+
 int key_bits(int64_t nkeys) {
   int b = 1;
   while (b < 32 && ((int64_t)1 << b) < nkeys) ++b;
@@ -597,6 +629,12 @@ kmeans_finalize_kernel(int64_t dim, const float* __restrict__ sums, const float*
 
 }  // namespace
 
+// digit width of the radix passes: 8 bits unless bof_config.radix_max_bits asks for less (test knob: more passes)
+static int digit_bits(const bof_ctx* ctx) {
+  const int b = ctx->cfg.radix_max_bits;
+  return (b <= 0 || b > 8) ? 8 : b;
+}
+
 size_t csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz) {
   (void)m;
   (void)n;
@@ -604,11 +642,6 @@ size_t csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz) {
   return 6 * arr + counts_bytes(nnz) + 512;
 }
 
-// digit width of the radix passes: 8 bits unless bof_config.radix_max_bits asks for less (test knob: more passes)
-static int digit_bits(const bof_ctx* ctx) {
-  const int b = ctx->cfg.radix_max_bits;
-  return (b <= 0 || b > 8) ? 8 : b;
-}
 
 int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t nnz,
                    const int64_t* offs, const int32_t* idx, const float* vals, int64_t* offs_t,
@@ -652,6 +685,50 @@ int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t n
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 256), (int64_t)ctx->num_sms * 32);
   segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(final_keys, nnz, n, offs_t);
   BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
+  return BOF_OK;
+}
+
+
+// y = A^T x without atomics: products v * x[row] are sorted stably by column (the radix passes of the
+// transpose, one 32-bit payload) and every column sums its run in a fixed order.  accumulate: y += instead of y =.
+size_t spmv_t_workspace_bytes(int64_t n, int64_t nnz) {
+  const size_t arr = align_up((size_t)std::max<int64_t>(nnz, 1) * 4);
+  return 5 * arr + counts_bytes(nnz) + align_up((size_t)(n + 1) * 8) + 512;
+}
+
+int launch_spmv_t_sorted(bof_ctx* ctx, cudaStream_t s, int accumulate, int64_t m, int64_t n, int64_t nnz, const float* vals,
+                         const int32_t* idx, const int64_t* offs, const float* x, float* y, void* ws, size_t ws_bytes) {
+  BOF_REQUIRE(ctx, nnz >= 0 && nnz < (1ll << 32) - RS_TILE, "csrgemv 'T': nnz must be below 2^32");
+  if (nnz == 0 || m == 0) {
+    if (!accumulate) BOF_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s));
+    return BOF_OK;
+  }
+  BOF_REQUIRE(ctx, ws != nullptr && ws_bytes >= spmv_t_workspace_bytes(n, nnz), "csrgemv 'T': workspace too small");
+  const size_t arr = align_up((size_t)nnz * 4);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  uint32_t* prod0 = reinterpret_cast<uint32_t*>(base);
+  Triple X{reinterpret_cast<uint32_t*>(base + arr), reinterpret_cast<uint32_t*>(base + 2 * arr), nullptr};
+  Triple Y{reinterpret_cast<uint32_t*>(base + 3 * arr), reinterpret_cast<uint32_t*>(base + 4 * arr), nullptr};
+  uint32_t* counts = reinterpret_cast<uint32_t*>(base + 5 * arr);
+  int64_t* seg = reinterpret_cast<int64_t*>(base + 5 * arr + counts_bytes(nnz));
+  row_products_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, s>>>(m, vals, offs, x, prod0);
+  BOF_LAUNCH_CHECK(ctx, "row_products_kernel");
+  const int db = digit_bits(ctx), kb = key_bits(n);
+  const int passes = ceil_div(kb, db);
+  const uint32_t* kin = reinterpret_cast<const uint32_t*>(idx);
+  const uint32_t* pin = prod0;
+  for (int p = 0; p < passes; ++p) {
+    Triple dst = (p % 2 == 0) ? X : Y;
+    int rc = radix_pass(ctx, s, nnz, db * p, std::min(db, kb - db * p), kin, pin, nullptr, dst, counts);
+    if (rc) return rc;
+    kin = dst.key;
+    pin = dst.p1;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 256), (int64_t)ctx->num_sms * 32);
+  segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(kin, nnz, n, seg);
+  BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
+  segment_sum_kernel<<<(unsigned)ceil_div<int64_t>(n, 32), 256, 0, s>>>(n, seg, pin, y, accumulate);
+  BOF_LAUNCH_CHECK(ctx, "segment_sum_kernel");
   return BOF_OK;
 }
 

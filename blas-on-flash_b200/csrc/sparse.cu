@@ -630,7 +630,6 @@ int spmm_tma_launch(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t k, float al
   return BOF_OK;
 }
 
-constexpr int kSlotSpmmLong = 36;   // context slot: counters, deferred-row lists, grid-path partials
 
 template <int KV>
 int long_rows_launch(bof_ctx* ctx, cudaStream_t s, int grid, int64_t k, float alpha, const float* vals, const int32_t* idx,
@@ -785,15 +784,29 @@ int launch_add_outer_terms(bof_ctx* ctx, cudaStream_t s, float* C, int64_t rows,
 }
 
 int launch_spmv(bof_ctx* ctx, cudaStream_t s, char trans, int64_t m, int64_t n, const float* vals,
-                const int32_t* idx, const int64_t* offs, const float* x, float* y) {
+                const int32_t* idx, const int64_t* offs, const float* x, float* y, int64_t nnz) {
   // 'T' zeroes y first (src/blas/csrgemv.cpp:64); 't' accumulates into y as it is, which is
   // what a row-block pipeline needs for every block after the memset.
   if (trans == 'T' || trans == 't') {
-    if (trans == 'T') BOF_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s));
-    if (m == 0) return BOF_OK;
-    spmv_csr_t_kernel<16, 4><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
-    BOF_LAUNCH_CHECK(ctx, "spmv_csr_t_kernel");
-    return BOF_OK;
+    if (ctx->cfg.spmv_t_atomic != 0) {
+      if (trans == 'T') BOF_CUDA(ctx, cudaMemsetAsync(y, 0, (size_t)n * sizeof(float), s));
+      if (m == 0) return BOF_OK;
+      spmv_csr_t_kernel<16, 4><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);
+      BOF_LAUNCH_CHECK(ctx, "spmv_csr_t_kernel");
+      return BOF_OK;
+    }
+    if (nnz < 0 && m > 0) {   // device-tile callers hand over device offsets only: one small read-back
+      int64_t ends[2] = {0, 0};
+      BOF_CUDA(ctx, cudaMemcpyAsync(&ends[0], offs, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      BOF_CUDA(ctx, cudaMemcpyAsync(&ends[1], offs + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      BOF_CUDA(ctx, cudaStreamSynchronize(s));
+      nnz = ends[1] - ends[0];
+    }
+    nnz = std::max<int64_t>(nnz, 0);
+    const size_t wsb = spmv_t_workspace_bytes(n, nnz);
+    void* ws = nullptr;
+    { const int rc = slot_reserve(ctx, kSlotSpmvT, wsb, &ws); if (rc != BOF_OK) return rc; }
+    return launch_spmv_t_sorted(ctx, s, trans == 't' ? 1 : 0, m, n, nnz, vals, idx, offs, x, y, ws, wsb);
   }
   if (m == 0) return BOF_OK;
   spmv_csr_n_kernel<16, 4><<<(unsigned)ceil_div<int64_t>(m, 16), 256, 0, s>>>(m, vals, idx, offs, x, y);

@@ -311,6 +311,10 @@ int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const flo
     BOF_TRY(slot_reserve(ctx, S_IDX32 + g, (size_t)max_nnz, &idx32_d[g]));
     BOF_TRY(slot_reserve(ctx, S_VALS + g, (size_t)max_nnz, &vals_d[g]));
   }
+  if (tr && ctx->cfg.spmv_t_atomic == 0) {   // workspace of the sorted A^T x path for the largest block, before the pipeline starts
+    void* wsp = nullptr;
+    BOF_TRY(slot_reserve(ctx, kSlotSpmvT, spmv_t_workspace_bytes(n, max_nnz), &wsp));
+  }
   bool used[2] = {false, false};
   for (int i = 0; i < nblk; ++i) {
     const int g = i & 1;
@@ -328,7 +332,7 @@ int bof_host_csrgemv(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, const flo
       BOF_TRY(launch_spmv(ctx, ctx->compute, 'N', rows, n, vals_d[g], idx32_d[g], offs_d[g], xd, yd + r0));
     } else {
       // y += A_blk^T x_blk : launch the accumulate kernel directly (y was zeroed once above)
-      BOF_TRY(launch_spmv(ctx, ctx->compute, 't', rows, n, vals_d[g], idx32_d[g], offs_d[g], xd + r0, yd));
+      BOF_TRY(launch_spmv(ctx, ctx->compute, 't', rows, n, vals_d[g], idx32_d[g], offs_d[g], xd + r0, yd, bnnz));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_done, ctx->compute));
     used[g] = true;
@@ -649,7 +653,7 @@ int bof_csr_mv(bof_csr* h, char trans_a, const float* x, float* y) {
   BOF_TRY(copy1d(ctx, xd, x, (size_t)xlen * 4, cudaMemcpyHostToDevice, s));
   if (!tr) BOF_TRY(launch_spmv(ctx, s, 'N', h->m, h->n, h->vals[0], h->idx[0], h->offs[0], xd, yd));
   else if (h->have_t) BOF_TRY(launch_spmv(ctx, s, 'N', h->n, h->m, h->vals[1], h->idx[1], h->offs[1], xd, yd));
-  else BOF_TRY(launch_spmv(ctx, s, 'T', h->m, h->n, h->vals[0], h->idx[0], h->offs[0], xd, yd));
+  else BOF_TRY(launch_spmv(ctx, s, 'T', h->m, h->n, h->vals[0], h->idx[0], h->offs[0], xd, yd, h->nnz));
   BOF_TRY(copy1d(ctx, y, yd, (size_t)ylen * 4, cudaMemcpyDeviceToHost, s));
   BOF_TRY(sync_all(ctx));
   stats_end(ctx);

@@ -73,6 +73,9 @@ typedef struct bof_config {
                                 error <= 2^-19 relative)                                          */
   int32_t radix_max_bits;    /* digit width of the csrcsc / k-means radix passes: 0 = default 8; smaller values
                                 force more passes (test knob)                                            */
+  int32_t spmv_t_atomic;     /* csrgemv 'T': 0 = default, deterministic (products sorted by column, fixed-order sums,
+                                no atomics); 1 = scatter with red.global.add.f32 (5x faster on the device, the
+                                order of the additions -- like the reference's mutex'd adds -- is not fixed)  */
 } bof_config;
 
 /* Per-stage accounting of the last host entry point, for the out-of-core roofline
@@ -125,8 +128,10 @@ BOF_API size_t bof_spmm_workspace_bytes(char ord, int64_t m, int64_t n, int64_t 
 /* K4/K5: y = op(A) x, y overwritten (no alpha/beta).
  * Replaces mkl_cspblas_scsrgemv in CsrGemvNoTransInMem::execute
  * (include/tasks/csrgemv_task.h:60-83) and CsrGemvTransInMem::execute (:152-179; the mutex'd
- * `out[i] += v_out[i]` becomes red.global.add.f32).  trans='N': x has n entries, y has m;
- * trans='T': x has m entries, y has n and is zeroed by the call (src/blas/csrgemv.cpp:64). */
+ * `out[i] += v_out[i]` in task-completion order becomes a deterministic sort-by-column + ordered column sums, or
+ * red.global.add.f32 with bof_config.spmv_t_atomic).  trans='N': x has n entries, y has m;
+ * trans='T': x has m entries, y has n and is overwritten (src/blas/csrgemv.cpp:64); it synchronises the stream once
+ * to read nnz from `offs` and takes its workspace from the context. */
 BOF_API int bof_spmv_csr_f32(bof_ctx* ctx, void* stream, char trans, int64_t m, int64_t n,
                      const float* vals, const int32_t* idx, const int64_t* offs, const float* x,
                      float* y);

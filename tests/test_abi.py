@@ -35,7 +35,7 @@ def test_abi_version(bof):
 
 def test_struct_layouts_match_header(bof):
     # bof_config: i32 i32 u64 i32 (pad) u64 u64 i32 i32 i32 i32 i32 (pad) ; bof_stats: 8 doubles + i64
-    assert C.sizeof(bof.BofConfig) == 64
+    assert C.sizeof(bof.BofConfig) == 64  # 13 x 4-byte + 3 x 8-byte fields with padding
     assert C.sizeof(bof.BofStats) == 72
 
 

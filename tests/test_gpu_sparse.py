@@ -265,3 +265,32 @@ def test_spmm_poisoned_unused_rows_of_b(ctx):
     ctx.spmm("R", m, n, k, 1.0, vals, idx, offs, dev(B), k, 0.0, Cd, k)
     Bz = B.copy(); Bz[0] = 0
     assert oracle.rel_fro(Cd.cpu().numpy(), oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", Bz, np.zeros((m, k), np.float32), acc64=True)) <= TOL
+
+
+def test_spmv_transposed_is_deterministic_and_atomic_free_by_default(bof, ctx):
+    """csrgemv 'T' (SURVEY K5): products sorted by column + fixed-order column sums -> bit-identical from run to run;
+    bof_config.spmv_t_atomic = 1 opts into the red.global.add scatter (tolerance-equal)"""
+    rng = np.random.default_rng(21)
+    m, n = 30000, 26000
+    a, ia, ja = ragged_csr(rng, m, n, 60)
+    x = rng.random(m, dtype=np.float32)
+    ref = oracle.csrgemv("T", m, n, a, ia, ja, x, acc64=True)
+    shift = 987654321   # un-rebased offsets: a row-block slice of a larger matrix
+    vals, idx, offs = csr_to_device(a, ia + shift, ja)
+    runs = []
+    for _ in range(3):
+        y = torch.full((n,), float("nan"), device="cuda")
+        ctx.spmv("T", m, n, vals, idx, offs, dev(x), y)
+        runs.append(y)
+        assert oracle.rel_fro(y.cpu().numpy(), ref) <= TOL
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    with bof.Context(device=0, spmv_t_atomic=1) as c2:
+        y = torch.full((n,), float("nan"), device="cuda")
+        c2.spmv("T", m, n, vals, idx, offs, dev(x), y)
+        assert oracle.rel_fro(y.cpu().numpy(), ref) <= TOL
+    # host pipeline, several row blocks accumulated in block order
+    with bof.Context(device=0, csrmm_max_nnz=200000) as c3:
+        y1 = np.full(n, np.nan, np.float32); y2 = np.full(n, np.nan, np.float32)
+        c3.host_csrgemv("T", m, n, a, ia, ja, x, y1)
+        c3.host_csrgemv("T", m, n, a, ia, ja, x, y2)
+        assert oracle.rel_fro(y1, ref) <= TOL and np.array_equal(y1, y2)

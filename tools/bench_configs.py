@@ -301,7 +301,16 @@ def cfg4(env: Env, host_csr, scale=1.0):
                "metric": "csrgemv_gflops", "value": 2.0 * nnz / t / 1e9, "unit": "GFLOP/s", "ms": t * 1e3,
                "roofline": {"bound": "hbm", "achieved": byts / t / 1e9, "peak": env.pk["hbm_gbs"], "unit": "GB/s",
                             "frac": byts / t / 1e9 / env.pk["hbm_gbs"], "model": "nnz*(4+4) + offsets + x + y (SURVEY.md 8d, I=4)",
-                            "traffic": ncu_traffic(f"spmv_{trans.lower()}_cfg4"), "kernel": f"spmv_csr_{trans.lower()}"}}
+                            "traffic": ncu_traffic(f"spmv_{trans.lower()}_cfg4"),
+                            "kernel": "spmv_csr_n_kernel" if trans == "N" else "row_products + radix passes + segment_sum (deterministic, no atomics)"}}
+        if trans == "T":
+            # the opt-in scatter kernel (red.global.add.f32, bof_config.spmv_t_atomic = 1) on the same buffers
+            with env.bof.Context(device=env.local, spmv_t_atomic=1) as ca:
+                ya = torch.empty_like(yv)
+                ta = env.time_gpu(lambda: ca.spmv(trans, mr, n, vals, idx, offs, xv, ya), iters=5, flush=True)
+            rec["atomic_variant"] = {"ms": ta * 1e3, "value": 2.0 * nnz / ta / 1e9, "frac": byts / ta / 1e9 / env.pk["hbm_gbs"],
+                                     "rel_fro_vs_default": float((ya.double() - yv.double()).norm() / yv.double().norm())}
+            del ya
         # parity on the timed buffer, fp64 on the device in chunks
         if trans == "N":
             rows = torch.from_numpy(np.random.default_rng(6).integers(0, mr, 4096)).to(env.dev)
