@@ -319,9 +319,16 @@ def run_extras(args, bof, ctx, torch, dist, pk, tf32, rank, world, local):
     host_csr = None
     if "cfg5" in want:
         extra["kmeans_cfg5"] = guarded("cfg5", lambda: bc.kmeans_cfg5(env, scale=args.scale))
+    if "file" in want and world == 1:
+        extra["e2e_file"] = guarded("file", lambda: bc.file_backed(env, scale=args.scale))
     if "pcie" in extra and "h2d_gbs_per_gpu" in extra["pcie"]:
         # out-of-core legs as multiples of the measured PCIe bound of THIS run (north_star: within 1.3x)
         h2d = extra["pcie"]["h2d_gbs_per_gpu"]
+        ef = extra.get("e2e_file", {})
+        if isinstance(ef.get("csrmm_cfg3"), dict) and "ms" in ef["csrmm_cfg3"]:
+            ef["csrmm_cfg3"]["x_of_pcie_bound"] = ef["csrmm_cfg3"]["ms"] / ((18.723e9) / h2d / 1e6)
+        if isinstance(ef.get("gemm_cfg2"), dict) and "ms" in ef["gemm_cfg2"]:
+            ef["gemm_cfg2"]["x_of_pcie_or_kernel_bound"] = ef["gemm_cfg2"]["ms"] / max(8.59e9 / h2d / 1e6, 201.0)
         for key, sub in (("csrmm_cfg3", "e2e"), ("csrmm_cfg3", "e2e_shared_b"), ("csrgemv_N_cfg4", "e2e")):
             e = extra.get(key, {}).get(sub)
             if e and e.get("h2d_bytes_per_step"):
@@ -343,7 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=M_FULL, help="override m=n=k (debug only; invalid as a bench value)")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--extra", default="pcie,cfg1,cfg3,cfg4,cfg5", help="which other configs to measure into `extra`")
+    ap.add_argument("--extra", default="pcie,cfg1,cfg3,cfg4,cfg5,file", help="which other configs to measure into `extra`")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg-3/4/5 (debug only; invalid as a bench value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on all CPUs (A/B of the NUMA binding)")

@@ -304,7 +304,7 @@ int ensure_ring(bof_ctx* ctx, std::vector<StageSlot>& ring) {
 // of the base).  With BOF_STAGE_FD=1 staging copies for such ranges use pread/pwrite on the descriptor instead
 // of touching the mapping (the reference's FlashFileHandle::read/write into cache buffers); the page cache keeps
 // both views coherent.
-struct FileRange { size_t len; int fd; uint64_t file_off; };
+struct FileRange { size_t len; int fd; uint64_t file_off; bool pinned = false; };
 std::mutex g_map_mu;
 std::map<uintptr_t, FileRange> g_mappings;
 
@@ -577,16 +577,52 @@ using namespace bof;
 
 extern "C" {
 
+// BOF_PIN_MAPPINGS=0 switches the page-locking of file mappings off (staging through the pinned ring is used then)
+static bool pin_mappings() {
+  static const bool on = [] { const char* e = getenv("BOF_PIN_MAPPINGS"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+
 int bof_register_mapping(const void* base, size_t len, int fd, uint64_t file_offset) {
   if (base == nullptr || len == 0 || fd < 0) return BOF_EINVAL;
+  FileRange fr{len, fd, file_offset};
+  // Page-lock the mapping and make it DMA-able: the page-cache pages behind a MAP_SHARED mapping are then what the
+  // copy engines read and write -- file -> HBM and HBM -> file without the pinned bounce buffer, the host memcpy and
+  // the page faults of a fresh mapping inside the timed call (the faults happen here, once, at map time).  The
+  // counterpart of the reference's O_DIRECT reads into its own aligned buffers
+  // (src/file_handles/flash_file_handle.cpp:247-407), minus the buffer.  Needs a current CUDA context (flash_setup
+  // creates it before the files are mapped); on failure -- no context, locked-memory limit, a filesystem whose pages
+  // cannot be pinned -- the mapping simply stays pageable and is staged as before.
+  int ndev = 0;
+  if (pin_mappings() && cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+    const double t0 = now_ms();
+    cudaError_t e = cudaHostRegister(const_cast<void*>(base), len, cudaHostRegisterPortable);
+    if (e == cudaSuccess) {
+      fr.pinned = true;
+      if (trace_on()) std::fprintf(stderr, "[bof host ] mapping of %zu bytes page-locked in %.1f ms\n", len, now_ms() - t0);
+    } else {
+      cudaGetLastError();
+      if (trace_on()) std::fprintf(stderr, "[bof host ] cudaHostRegister of a %zu-byte mapping failed (%s): staged copies\n", len, cudaGetErrorString(e));
+    }
+  } else {
+    cudaGetLastError();
+  }
   std::lock_guard<std::mutex> lk(g_map_mu);
-  g_mappings[reinterpret_cast<uintptr_t>(base)] = FileRange{len, fd, file_offset};
+  g_mappings[reinterpret_cast<uintptr_t>(base)] = fr;
   return BOF_OK;
 }
 
 int bof_unregister_mapping(const void* base) {
   std::lock_guard<std::mutex> lk(g_map_mu);
-  return g_mappings.erase(reinterpret_cast<uintptr_t>(base)) ? BOF_OK : BOF_EINVAL;
+  auto it = g_mappings.find(reinterpret_cast<uintptr_t>(base));
+  if (it == g_mappings.end()) return BOF_EINVAL;
+  if (it->second.pinned) {
+    cudaDeviceSynchronize();   // nothing may still be reading or writing the pages
+    cudaHostUnregister(const_cast<void*>(base));
+    cudaGetLastError();
+  }
+  g_mappings.erase(it);
+  return BOF_OK;
 }
 
 }  // extern "C"
