@@ -47,7 +47,7 @@ if "--impl" in sys.argv and "reference" in sys.argv:
 M_FULL = N_FULL = K_FULL = 32768
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size gemm3xtf32_kernel launch, from the
 # ncu --set full capture summarised in profiles/ (None until that capture exists)
-NCU_TRAFFIC_BYTES = 275547808768 + 4636467712  # profiles/r01/ncu_gemm32k_hybrid.csv (trip 9)
+NCU_TRAFFIC_BYTES = 275551000000 + 4630000000  # profiles/r02/t14_per_launch_all_configs.txt (gemm3xtf32_kernel<2,0,1,1>, one launch)
 TILE = 8192  # reference GEMM_BLK_SIZE (CMakeLists.txt:46-50 of the reference)
 
 

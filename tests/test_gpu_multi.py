@@ -115,3 +115,33 @@ def test_dist_paths_under_torchrun():
                         "--master-port", "29533", str(ROOT / "tools" / "dist_check.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"comm_world": %d' % n in r.stdout
+
+
+@need2
+def test_cpp_drivers_with_bof_gpus(tmp_path):
+    """BOF_GPUS=n: the unchanged C++ drivers (reference CLIs, file-backed flash_ptrs) spread over the GPUs"""
+    import __graft_entry__ as g
+    binp = ROOT / "build"
+    if not (binp / "gemm").exists():
+        g.build()
+    env = dict(os.environ, BOF_GPUS=str(min(NGPU, 4)))
+    rng = np.random.default_rng(3)
+    M, N, K = 3000, 2200, 1600
+    A = rng.random((M, K), dtype=np.float32); B = rng.random((K, N), dtype=np.float32); C0 = rng.random((M, N), dtype=np.float32)
+    A.tofile(tmp_path / "A.bin"); B.tofile(tmp_path / "B.bin"); C0.tofile(tmp_path / "C.bin")
+    r = subprocess.run([str(binp / "gemm"), *map(str, (tmp_path / "A.bin", tmp_path / "B.bin", tmp_path / "C.bin", M, K, N, 1.0, 0.5,
+                                                      "N", "N", "R", 0, 0, 0))], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "returned 0" in r.stdout, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "C.bin", dtype=np.float32).reshape(M, N)
+    assert oracle.rel_fro(got, oracle.gemm("R", "N", "N", M, N, K, 1.0, 0.5, A, B, C0, acc64=True)) <= TOL
+    m, n, k = 40000, 30000, 64
+    av, ia, ja = oracle.gen_csr(m, n, 18, seed=5)
+    Bd = oracle.gen_dense((n, k), seed=6); Cd = oracle.gen_dense((m, k), seed=7)
+    av.tofile(tmp_path / "A.csr"); ja.tofile(tmp_path / "A.col"); ia.tofile(tmp_path / "A.off")
+    Bd.tofile(tmp_path / "B2.bin"); Cd.tofile(tmp_path / "C2.bin")
+    r = subprocess.run([str(binp / "csrmm"), *map(str, (tmp_path / "A.csr", tmp_path / "A.col", tmp_path / "A.off", tmp_path / "B2.bin",
+                                                       tmp_path / "C2.bin", m, n, k, 1.0, 0.5, "N", "R"))], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "returned 0" in r.stdout, r.stdout + r.stderr
+    got = np.fromfile(tmp_path / "C2.bin", dtype=np.float32).reshape(m, k)
+    assert oracle.rel_fro(got, oracle.csrmm("N", m, n, k, 1.0, 0.5, av, ia, ja, "R", Bd, Cd, acc64=True)) <= TOL
