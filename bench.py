@@ -445,6 +445,25 @@ def main():
                              f"{'sustained' if long_run else 'burst'} {bf16_peak:.0f}, TF32 = cuBLAS TF32 8192^3 measured in this "
                              f"run (burst {tf32['burst']:.0f}, sustained {tf32['sustained']:.0f} TFLOP/s; the file has no TF32 entry)",
                 "alt_peak_3xtf32": tf32_peak / 3.0, "alt_frac_3xtf32": achieved / (tf32_peak / 3.0), "peaks_file": pk["src"]}
+    # The same fractions against THIS library's own instructions: tc_issue_rate_kernel issues the product kernel's MMAs
+    # (cta_group::2, 256x256 TMEM accumulator) back to back on one resident smem stage.  Burst = one 4000-round launch,
+    # sustained = back-to-back launches for ~2 s (power cap).
+    try:
+        own = {}
+        for kind, name in ((0, "tf32"), (1, "bf16"), (2, "hybrid_useful")):
+            burst = ctx.tc_issue_rate(kind, 4000)[1 if kind == 2 else 0]
+            t_end, vals = time.time() + 2.0, []
+            while time.time() < t_end:
+                vals.append(ctx.tc_issue_rate(kind, 40000)[1 if kind == 2 else 0])
+            own[name] = {"burst": burst, "sustained": sum(vals[len(vals) // 2:]) / max(1, len(vals) - len(vals) // 2)}
+        which = "sustained" if long_run else "burst"
+        roofline["own_peaks_tflops"] = own
+        roofline["frac_hybrid"] = achieved / own["hybrid_useful"][which]       # of the issue-rate ceiling of the actual MMA mix
+        roofline["frac_3xtf32"] = achieved / (own["tf32"][which] / 3.0)         # TF32 peak / 3
+        roofline["own_peaks_note"] = ("bof_tc_issue_rate: kind::tf32 / kind::f16(bf16) MMA flops and, for the hybrid mix, useful fp32 flops "
+                                      f"(1/3 of the MMA work); fractions use the {which} figures")
+    except Exception as ex:
+        roofline["own_peaks_error"] = repr(ex)[:200]
     # spot check of the result on the timed buffers (cheap: 64 sampled entries in fp64)
     ii = torch.randint(0, Mr, (64,), device="cuda"); jj = torch.randint(0, Ng, (64,), device="cuda")
     ref = (A[ii].double() * B[:, jj].t().double()).sum(1)

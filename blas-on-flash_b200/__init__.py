@@ -99,6 +99,12 @@ class Context:
         self._check(self.lib.bof_sgemm_f32(self.h, stream or _cur_stream(), ch(ord_), ch(ta), ch(tb), m, n, k, alpha,
                                            ptr(A), lda, ptr(B), ldb, beta, ptr(Cmat), ldc, ptr(ws), ws.numel()))
 
+    def tc_issue_rate(self, kind: int, rounds: int = 20000, stream=None):
+        """(mma_tflops, useful_tflops) of the tensor-pipe issue-rate microbenchmark; kind 0 tf32, 1 bf16, 2 hybrid mix"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.bof_tc_issue_rate(self.h, stream or _cur_stream(), kind, rounds, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def csr2csc_workspace(self, m, n, nnz):
         return self._ws(self.lib.bof_csr2csc_workspace_bytes(m, n, nnz))
 

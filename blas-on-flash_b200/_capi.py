@@ -68,6 +68,7 @@ PROTOTYPES = {
     "bof_sgemm_f32": (C.c_int, [_vp, _vp, _ch, _ch, _ch, _i64, _i64, _i64, _f32, _vp, _i64, _vp, _i64, _f32,
                                 _vp, _i64, _vp, _sz]),
     "bof_sgemm_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "bof_tc_issue_rate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bof_csr2csc": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
     "bof_csr2csc_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "bof_row_sqnorm_f32": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),

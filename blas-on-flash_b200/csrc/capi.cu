@@ -167,6 +167,12 @@ int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb, int64_
   return gemm_canon_device(ctx, as_stream(stream), c, alpha, beta, C, workspace, workspace_bytes);
 }
 
+int bof_tc_issue_rate(bof_ctx* ctx, void* stream, int kind, int rounds, double* mma_tflops, double* useful_tflops) {
+  if (!ctx) return BOF_EINVAL;
+  BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+  return tc_issue_rate(ctx, as_stream(stream), kind, rounds, mma_tflops, useful_tflops);
+}
+
 size_t bof_csr2csc_workspace_bytes(int64_t m, int64_t n, int64_t nnz) { return csr2csc_workspace_bytes(m, n, nnz); }
 
 int bof_csr2csc(bof_ctx* ctx, void* stream, int64_t m, int64_t n, int64_t nnz, const int64_t* offs,

@@ -199,6 +199,8 @@ int launch_gemm_tc(bof_ctx* ctx, cudaStream_t s, int cta_group, int64_t M, int64
                    int64_t kp, const float* p_hi, const float* p_lo, const float* q_hi,
                    const float* q_lo, const GemmEpilogue& ep, int64_t k_chunk);
 
+int tc_issue_rate(bof_ctx* ctx, cudaStream_t s, int kind, int rounds, double* mma_tflops, double* useful_tflops);
+
 // CUDA-core fp32 GEMM for ragged / unaligned shapes: C[i*ldc+j] = alpha*sum_k A(i,k)*B(k,j) +
 // beta*C with A(i,k) = A[i*a_r + k*a_k], B(k,j) = B[k*b_k + j*b_c].
 int launch_gemm_ffma(bof_ctx* ctx, cudaStream_t s, int64_t M, int64_t N, int64_t K, float alpha,

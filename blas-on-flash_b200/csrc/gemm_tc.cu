@@ -570,6 +570,69 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_p_hi, const __grid_con
   if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe issue-rate microbenchmark: the roofline denominator, measured with this library's own instructions.
+// Every CTA pair issues the GEMM's MMAs (cta_group::2, 256 x 256 accumulator in TMEM) back to back on ONE resident
+// shared-memory stage -- no TMA traffic, no epilogue -- so the number is what the tensor pipe sustains when nothing
+// else is in its way: kind 0 = kind::tf32 only, 1 = kind::f16 (bf16) only, 2 = the hybrid mix of the product kernel
+// (per 32 k-elements: four bf16 MMAs of K = 16 for the two cross terms + four tf32 MMAs of K = 8 for hi*hi).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+tc_issue_rate_kernel(int kind, int rounds) {
+  constexpr int CG = 2;
+  constexpr int BLOCK_N = 256;
+  constexpr uint32_t IDESC = make_idesc(BLOCK_M * CG, BLOCK_N, 2u);
+  constexpr uint32_t IDESC_BF16 = make_idesc(BLOCK_M * CG, BLOCK_N, 1u);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_leader = cluster_ctarank() == 0;
+  // operand planes: small integers as fp32 / bf16 bit patterns (finite, not all zero)
+  uint32_t* w = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < STAGE_BYTES / 4; i += blockDim.x) w[i] = 0x3f800000u + ((i * 2654435761u) & 0x007f0000u);
+  if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_barrier_init(); }
+  if (warp == 2) tmem_alloc<CG>(&tmem_base_s, 2 * BLOCK_N);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes visible to the MMA's async proxy
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  if (warp == 1 && is_leader) {
+    if (lane == 0) {
+      const uint32_t st = smem_u32(smem);
+      const uint64_t d_p_hi = make_smem_desc(st), d_p_lo = make_smem_desc(st + PLANE_BYTES);
+      const uint64_t d_q_hi = make_smem_desc(st + 2 * PLANE_BYTES), d_q_lo = make_smem_desc(st + 3 * PLANE_BYTES);
+      for (int r = 0; r < rounds; ++r) {
+        if (kind != 0) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            umma_bf16<CG>(tmem_d, d_p_lo + 4 + adv, d_q_lo + adv, IDESC_BF16, (r | kk) == 0 ? 0u : 1u);
+            umma_bf16<CG>(tmem_d, d_p_lo + adv, d_q_lo + 4 + adv, IDESC_BF16, 1u);
+          }
+        }
+        if (kind != 1) {
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
+            umma_tf32<CG>(tmem_d, d_p_hi + adv, d_q_hi + adv, IDESC, (kind == 0 && (r | kk) == 0) ? 0u : 1u);
+          }
+        }
+      }
+      umma_commit<CG>(&done_bar);
+    }
+    __syncwarp();
+  }
+  // both CTAs wait for the pair's MMAs (the commit is multicast to the same barrier offset in both)
+  if (warp == 0) mbar_wait(&done_bar, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc<CG>(tmem_d, 2 * BLOCK_N);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -886,6 +949,46 @@ int launch_gemm_ffma(bof_ctx* ctx, cudaStream_t s, int64_t M, int64_t N, int64_t
   BOF_REQUIRE(ctx, grid.y <= 65535u, "gemm_ffma: too many row tiles (use the tensor-core path)");
   gemm_ffma_kernel<<<grid, 256, 0, s>>>(M, N, K, alpha, A, a_r, a_k, B, b_k, b_c, beta, C, ldc);
   BOF_LAUNCH_CHECK(ctx, "gemm_ffma_kernel");
+  return BOF_OK;
+}
+
+
+// tensor-pipe issue rate in TFLOP/s of MMA work (2 * M * N * K per instruction) for `kind` (see tc_issue_rate_kernel);
+// `useful` additionally returns the rate in USEFUL fp32 flops of the hybrid mix (2 * 256 * 256 * 32 per round)
+int tc_issue_rate(bof_ctx* ctx, cudaStream_t s, int kind, int rounds, double* mma_tflops, double* useful_tflops) {
+  BOF_REQUIRE(ctx, kind >= 0 && kind <= 2 && rounds > 0, "tc_issue_rate: bad kind / rounds");
+  static PerDeviceOnce attr_set;
+  const size_t smem = (size_t)tc::STAGE_BYTES + 2048;
+  if (attr_set.need(ctx->device)) {
+    BOF_CUDA(ctx, cudaFuncSetAttribute(tc::tc_issue_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.done(ctx->device);
+  }
+  const int clusters = ctx->num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  BOF_CUDA(ctx, cudaEventCreate(&e0));
+  BOF_CUDA(ctx, cudaEventCreate(&e1));
+  BOF_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc::tc_issue_rate_kernel, kind, 64));   // warm-up
+  BOF_CUDA(ctx, cudaEventRecord(e0, s));
+  BOF_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc::tc_issue_rate_kernel, kind, rounds));
+  BOF_LAUNCH_CHECK(ctx, "tc_issue_rate_kernel");
+  BOF_CUDA(ctx, cudaEventRecord(e1, s));
+  BOF_CUDA(ctx, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  BOF_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double per_round_useful = 2.0 * 256 * 256 * 32;                     // one 32-element k-step of a 256 x 256 tile
+  const double mma_per_round = per_round_useful * (kind == 2 ? 3.0 : 1.0);  // hybrid: hi*hi + two cross terms
+  if (mma_tflops) *mma_tflops = mma_per_round * rounds * clusters / (ms * 1e-3) / 1e12;
+  if (useful_tflops) *useful_tflops = per_round_useful * rounds * clusters / (ms * 1e-3) / 1e12;
   return BOF_OK;
 }
 

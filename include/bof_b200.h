@@ -150,6 +150,12 @@ BOF_API int bof_sgemm_f32(bof_ctx* ctx, void* stream, char ord, char ta, char tb
                   int64_t ldb, float beta, float* C, int64_t ldc, void* workspace,
                   size_t workspace_bytes);
 BOF_API size_t bof_sgemm_workspace_bytes(int64_t m, int64_t n, int64_t k);
+/* Measurement aid (no reference counterpart): what the tensor pipe sustains for this library's own MMA instructions,
+ * issued back to back by every CTA pair on one resident shared-memory stage (no TMA, no epilogue).  kind 0 =
+ * kind::tf32, 1 = kind::f16 on bf16, 2 = the hybrid mix of the product kernel.  *mma_tflops counts 2*M*N*K per MMA,
+ * *useful_tflops counts the fp32-equivalent flops of the mix (kind 2: one third of the MMA work).  Synchronises. */
+BOF_API int bof_tc_issue_rate(bof_ctx* ctx, void* stream, int kind, int rounds, double* mma_tflops,
+                      double* useful_tflops);
 
 /* K6/K7: stable CSR -> CSC (A m x n  ->  A^T as CSR n x m): per output row ascending source
  * row, duplicates in storage order.  Replaces mkl_scsrcsc + index rebase in
