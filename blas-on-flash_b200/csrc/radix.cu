@@ -62,8 +62,12 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d) {
 // One block of 128 threads per scatter tile.
 constexpr int RH_THREADS = 128;
 constexpr int RH_WARPS = RH_THREADS / 32;
-constexpr int RH_IPT = RS_TILE / RH_THREADS;  // 32 keys per thread
-static_assert(RH_IPT <= 255, "one-byte counters");
+constexpr int RH_IPT = RS_TILE / RH_THREADS;  // 32 keys per thread and tile
+// A block owns a SUPERTILE of RS_SUPER consecutive tiles (histogram: one set of counters for all of them; scatter:
+// a running output cursor per digit carried from tile to tile): 4x fewer counters to scan and the per-block set-up
+// (zeroing / reducing 32 KiB of byte counters) amortised over 16384 keys.
+constexpr int RS_SUPER = 4;
+static_assert(RH_IPT * RS_SUPER <= 255, "one-byte counters");
 
 __global__ void __launch_bounds__(RH_THREADS)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, uint32_t mask,
@@ -73,18 +77,22 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, uint3
   uint4* z = reinterpret_cast<uint4*>(&cnt8[0][0][0]);
   for (int i = threadIdx.x; i < (int)(sizeof(cnt8) / 16); i += RH_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const int64_t warp_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * 32 * RH_IPT;
-  uint32_t k[8];
-  for (int r0 = 0; r0 < RH_IPT; r0 += 8) {
+  for (int t = 0; t < RS_SUPER; ++t) {
+    const int64_t tile_base = ((int64_t)blockIdx.x * RS_SUPER + t) * RS_TILE;
+    if (tile_base >= n) break;
+    const int64_t warp_base = tile_base + (int64_t)warp * 32 * RH_IPT;
+    uint32_t k[8];
+    for (int r0 = 0; r0 < RH_IPT; r0 += 8) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t i = warp_base + (r0 + u) * 32 + lane;
-      k[u] = (i < n) ? __ldcs(keys + i) : 0xffffffffu;
-    }
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = warp_base + (r0 + u) * 32 + lane;
+        k[u] = (i < n) ? __ldcs(keys + i) : 0xffffffffu;
+      }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t i = warp_base + (r0 + u) * 32 + lane;
-      if (i < n) cnt8[warp][(k[u] >> shift) & mask][lane]++;
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = warp_base + (r0 + u) * 32 + lane;
+        if (i < n) cnt8[warp][(k[u] >> shift) & mask][lane]++;
+      }
     }
   }
   __syncthreads();
@@ -182,8 +190,9 @@ struct ScatterSmem {
   uint16_t sdig[RS_TILE];
   uint32_t cnt[RS_WARPS][RS_CNT_STRIDE];
   uint32_t digit_off[RS_BINS + 1];   // start of each digit inside the block-sorted tile
-  uint32_t gbase[RS_BINS];           // global start of (digit, this tile); later minus digit_off:
+  uint32_t gbase[RS_BINS];           // global start of (digit, this tile) minus digit_off:
                                      // global position of tile slot s = gbase[digit(s)] + s
+  uint32_t run[RS_BINS];             // running global cursor of every digit across the tiles of the supertile
 };
 
 // Stable scatter of one tile.  offsets = exclusive scan of the histogram kernel's counts.
@@ -200,11 +209,14 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(rs_smem_raw);
   RowSmem& rs = *reinterpret_cast<RowSmem*>(rs_smem_raw + ((sizeof(ScatterSmem) + 15) & ~(size_t)15));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < RS_BINS) sm.run[threadIdx.x] = offsets[(size_t)threadIdx.x * num_tiles + blockIdx.x];
+  for (int tile = 0; tile < RS_SUPER; ++tile) {
+  const int64_t tile_base = ((int64_t)blockIdx.x * RS_SUPER + tile) * RS_TILE;
+  if (tile_base >= n) break;
+  __syncthreads();   // the previous tile's staging buffer, counters and cursors are no longer in use
   for (int i = threadIdx.x; i < RS_WARPS * RS_CNT_STRIDE; i += RS_THREADS) (&sm.cnt[0][0])[i] = 0;
-  if (threadIdx.x < RS_BINS) sm.gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * num_tiles + blockIdx.x];
   __syncthreads();
 
-  const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
   const int64_t warp_base = tile_base + (int64_t)warp * 32 * RS_IPT;
   const int tile_count = (int)min((int64_t)RS_TILE, n - tile_base);
 
@@ -266,7 +278,10 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     const uint32_t d = digit_of(r);
     slot[r] = (d < 256u) ? sm.digit_off[d] + sm.cnt[warp][d] + slot[r] : NO_SLOT;
   }
-  if (threadIdx.x < RS_BINS) sm.gbase[threadIdx.x] -= sm.digit_off[threadIdx.x];  // wraps mod 2^32, undone by + s
+  if (threadIdx.x < RS_BINS) {
+    sm.gbase[threadIdx.x] = sm.run[threadIdx.x] - sm.digit_off[threadIdx.x];  // wraps mod 2^32, undone by + s
+    sm.run[threadIdx.x] += sm.digit_off[threadIdx.x + 1] - sm.digit_off[threadIdx.x];   // next tile of the supertile
+  }
 
   // keys: local sort into smem, then contiguous runs to global
 #pragma unroll
@@ -296,6 +311,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict_
     for (int s = threadIdx.x; s < tile_count; s += RS_THREADS)
       pout[(uint32_t)(sm.gbase[sm.sdig[s]] + (uint32_t)s)] = sm.stage[s];
   }
+  }  // tiles of the supertile
 }
 
 // ---- device-wide exclusive scan of uint32 (in place), three kernels ---------------------------
@@ -377,13 +393,29 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 segment_offsets_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, int64_t nseg,
                        OutT* __restrict__ seg_offs) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
-    // keys above nseg (never produced by our kernels; a caller-supplied assignment could hold one) must not
-    // run the loop past the (nseg + 1)-entry output
-    const int64_t lo = (i == 0) ? 0 : (int64_t)sorted_keys[i - 1] + 1;
-    const int64_t hi = (i == n) ? nseg : min((int64_t)sorted_keys[i], nseg);
-    for (int64_t c = lo; c <= hi; ++c) seg_offs[c] = (OutT)i;
+  // four consecutive positions per thread (one 16-byte load when aligned); position i closes the segments of the
+  // keys in (key[i-1], key[i]]
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 <= n; i0 += stride) {
+    uint32_t k[5];
+    k[0] = i0 == 0 ? 0u : sorted_keys[i0 - 1];
+    if (i0 + 4 <= n && (reinterpret_cast<uintptr_t>(sorted_keys + i0) & 15) == 0) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sorted_keys + i0));
+      k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) k[1 + u] = (i0 + u < n) ? sorted_keys[i0 + u] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u;
+      if (i > n) break;
+      // keys above nseg (never produced by our kernels; a caller-supplied assignment could hold one) must not
+      // run the loop past the (nseg + 1)-entry output
+      const int64_t lo = (i == 0) ? 0 : (int64_t)k[u] + 1;
+      const int64_t hi = (i == n) ? nseg : min((int64_t)k[1 + u], nseg);
+      for (int64_t c = lo; c <= hi; ++c) seg_offs[c] = (OutT)i;
+    }
   }
 }
 
@@ -433,7 +465,7 @@ int key_bits(int64_t nkeys) {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t counts_bytes(int64_t n) {
-  const int64_t tiles = ceil_div<int64_t>(std::max<int64_t>(n, 1), RS_TILE);
+  const int64_t tiles = ceil_div<int64_t>(std::max<int64_t>(n, 1), (int64_t)RS_TILE * RS_SUPER);
   const int64_t ncounts = tiles * RS_BINS;
   const int64_t nblocks = ceil_div<int64_t>(ncounts, SC_CHUNK);
   return align_up((size_t)ncounts * 4) + align_up((size_t)nblocks * 4);
@@ -460,7 +492,7 @@ struct Triple {
 int radix_pass(bof_ctx* ctx, cudaStream_t s, int64_t n, int shift, int bits, const uint32_t* key_in,
                const uint32_t* p1_in, const uint32_t* p2_in, Triple out, uint32_t* counts,
                const int64_t* row_offs = nullptr, int64_t m = 0) {
-  const int64_t tiles = ceil_div<int64_t>(n, RS_TILE);
+  const int64_t tiles = ceil_div<int64_t>(n, (int64_t)RS_TILE * RS_SUPER);   // supertiles: one block each
   const int64_t ncounts = tiles * RS_BINS;
   uint32_t* block_sums = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(counts) + align_up((size_t)ncounts * 4));
   const uint32_t mask = (1u << bits) - 1u;
@@ -682,7 +714,7 @@ int launch_csr2csc(bof_ctx* ctx, cudaStream_t s, int64_t m, int64_t n, int64_t n
     rin = dst.p1;
     vin = dst.p2;
   }
-  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 256), (int64_t)ctx->num_sms * 32);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 1024), (int64_t)ctx->num_sms * 32);
   segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(final_keys, nnz, n, offs_t);
   BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
   return BOF_OK;
@@ -724,7 +756,7 @@ int launch_spmv_t_sorted(bof_ctx* ctx, cudaStream_t s, int accumulate, int64_t m
     kin = dst.key;
     pin = dst.p1;
   }
-  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 256), (int64_t)ctx->num_sms * 32);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(nnz + 1, 1024), (int64_t)ctx->num_sms * 32);
   segment_offsets_kernel<int64_t><<<grid, 256, 0, s>>>(kin, nnz, n, seg);
   BOF_LAUNCH_CHECK(ctx, "segment_offsets_kernel");
   segment_sum_kernel<<<(unsigned)ceil_div<int64_t>(n, 32), 256, 0, s>>>(n, seg, pin, y, accumulate);
