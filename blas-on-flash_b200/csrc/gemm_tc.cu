@@ -986,7 +986,8 @@ int tc_issue_rate(bof_ctx* ctx, cudaStream_t s, int kind, int rounds, double* mm
   BOF_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   const double per_round_useful = 2.0 * 256 * 256 * 32;                     // one 32-element k-step of a 256 x 256 tile
-  const double mma_per_round = per_round_useful * (kind == 2 ? 3.0 : 1.0);  // hybrid: hi*hi + two cross terms
+  // MMA work per round: tf32 = one term, bf16 = the two cross terms, hybrid = all three
+  const double mma_per_round = per_round_useful * (kind == 2 ? 3.0 : (kind == 1 ? 2.0 : 1.0));
   if (mma_tflops) *mma_tflops = mma_per_round * rounds * clusters / (ms * 1e-3) / 1e12;
   if (useful_tflops) *useful_tflops = per_round_useful * rounds * clusters / (ms * 1e-3) / 1e12;
   return BOF_OK;

@@ -63,10 +63,13 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d) {
 constexpr int RH_THREADS = 128;
 constexpr int RH_WARPS = RH_THREADS / 32;
 constexpr int RH_IPT = RS_TILE / RH_THREADS;  // 32 keys per thread and tile
-// A block owns a SUPERTILE of RS_SUPER consecutive tiles (histogram: one set of counters for all of them; scatter:
-// a running output cursor per digit carried from tile to tile): 4x fewer counters to scan and the per-block set-up
-// (zeroing / reducing 32 KiB of byte counters) amortised over 16384 keys.
-constexpr int RS_SUPER = 4;
+// A block can own a SUPERTILE of RS_SUPER consecutive tiles (histogram: one set of counters for all of them; scatter:
+// a running output cursor per digit carried from tile to tile).  Measured at cfg-4 with RS_SUPER = 4
+// (profiles/r02/t15_csrcsc_supertile4_per_launch.txt): histogram 1.75 -> 1.13 ms and the scans vanish, but the scatter
+// passes go from 8.9 / 7.3 / 6.9 ms to 12.0 / 13.3 / 9.3 ms with 40-60 % more DRAM traffic -- adjacent output regions
+// are then written by ONE block minutes of GPU time apart instead of by neighbouring blocks at the same time, and L2
+// evicts the partially written sectors in between.  So: one tile per block.
+constexpr int RS_SUPER = 1;
 static_assert(RH_IPT * RS_SUPER <= 255, "one-byte counters");
 
 __global__ void __launch_bounds__(RH_THREADS)
