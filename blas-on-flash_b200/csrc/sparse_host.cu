@@ -29,8 +29,11 @@ extern "C" {
 
 static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
                            const float* a, const int64_t* ia, const int64_t* ja, char ord_b, const float* b, float* c,
-                           const float* b_dev, bool dist_b = false) {
+                           const float* b_dev, bool dist_b = false, int64_t ldk = 0) {
+  // ldk: leading dimension of the host B and C when this call works on a column panel of a wider product
+  // (row-major, trans_a = 'N' only); 0 = tight (k)
   if (!ctx) return BOF_EINVAL;
+  if (ldk == 0) ldk = k;
   BOF_REQUIRE(ctx, is_nt(trans_a), "csrmm: unrecognized value for param trans_a = '%c'", trans_a);
   BOF_REQUIRE(ctx, b_dev == nullptr || (trans_a == 'N' && ord_b == 'R'),
               "csrmm: a device-resident B is supported for trans_a='N', ord_b='R' only");
@@ -106,7 +109,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
     BOF_TRY(launch_transpose(ctx, ctx->compute, k, in_rows, Braw, in_rows, Bd, k));
   } else {
-    BOF_TRY(copy1d(ctx, Bd, b, (size_t)in_rows * k * 4, H2D, ctx->h2d));
+    BOF_TRY(copy2d(ctx, Bd, (size_t)k * 4, b, (size_t)ldk * 4, (size_t)k * 4, (size_t)in_rows, H2D, ctx->h2d));
     cudaEvent_t evB = get_event(ctx, 0);
     BOF_CUDA(ctx, cudaEventRecord(evB, ctx->h2d));
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
@@ -216,7 +219,7 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     float* c_io = colmaj ? cblk_t[g] : cblk[g];
     if (beta != 0.f) {
       if (colmaj) BOF_TRY(copy2d(ctx, c_io, (size_t)rows * 4, c + r0, (size_t)m * 4, (size_t)rows * 4, (size_t)k, H2D, ctx->h2d));
-      else BOF_TRY(copy1d(ctx, c_io, c + r0 * k, (size_t)rows * k * 4, H2D, ctx->h2d));
+      else BOF_TRY(copy2d(ctx, c_io, (size_t)k * 4, c + r0 * ldk, (size_t)ldk * 4, (size_t)k * 4, (size_t)rows, H2D, ctx->h2d));
     }
     BOF_CUDA(ctx, cudaEventRecord(ev_up, ctx->h2d));
     trace_mark(ctx, ctx->h2d, "h2d: A block landed", i);
@@ -241,7 +244,8 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     float* c_io = colmaj ? cblk_t[g] : cblk[g];
     cudaEvent_t ev_done = get_event(ctx, 6 + g), ev_down = get_event(ctx, 8 + g);
     if (colmaj) BOF_TRY(d2h_transfer(ctx, c + r0, (size_t)m * 4, c_io, (size_t)rows * 4, (size_t)rows * 4, (size_t)k, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
-    else BOF_TRY(d2h_transfer(ctx, c + r0 * k, (size_t)rows * k * 4, c_io, (size_t)rows * k * 4, (size_t)rows * k * 4, 1, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
+    else if (ldk == k) BOF_TRY(d2h_transfer(ctx, c + r0 * k, (size_t)rows * k * 4, c_io, (size_t)rows * k * 4, (size_t)rows * k * 4, 1, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
+    else BOF_TRY(d2h_transfer(ctx, c + r0 * ldk, (size_t)ldk * 4, c_io, (size_t)k * 4, (size_t)k * 4, (size_t)rows, ctx->d2h, ev_done, ev_down, &down_ticket[g]));
     trace_mark(ctx, ctx->d2h, "d2h: C block downloaded", i);
     return BOF_OK;
   };
@@ -256,8 +260,36 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   return call_guard.done();
 }
 
+// Widest column panel of B the device can hold next to the streamed blocks (0: the whole B fits).  The reference cuts B
+// into column blocks of CSRMM_RM_CBLK_SIZE = 1024 for the same reason, a memory budget (src/blas/csrmm.cpp:64-126,
+// include/tasks/csrmm_task.h:175-199); here the budget is HBM, and A is re-streamed once per panel.
+static int64_t csrmm_column_panel(bof_ctx* ctx, int64_t in_rows, int64_t k) {
+  static const int64_t forced = getenv("BOF_CSRMM_KPANEL") ? atoll(getenv("BOF_CSRMM_KPANEL")) : 0;   // test knob
+  if (forced > 0) return forced < k ? forced : 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const double budget = 0.6 * (double)total_b;
+  if ((double)in_rows * k * 4 <= budget) return 0;
+  int64_t kp = (int64_t)(budget / ((double)in_rows * 4));
+  kp = (kp / 32) * 32;
+  (void)ctx;
+  return kp >= 32 ? kp : 32;
+}
+
 int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, float alpha, float beta,
                    const float* a, const int64_t* ia, const int64_t* ja, char ord_b, const float* b, float* c) {
+  if (ctx && trans_a == 'N' && ord_b == 'R' && m >= 0 && n > 0 && k > 0) {
+    cudaSetDevice(ctx->device);
+    const int64_t kp = csrmm_column_panel(ctx, n, k);
+    if (kp > 0) {   // B does not fit in HBM: one pass over A per column panel of B and C
+      for (int64_t c0 = 0; c0 < k; c0 += kp) {
+        const int rc = host_csrmm_impl(ctx, 'N', m, n, std::min(kp, k - c0), alpha, beta, a, ia, ja, 'R', b + c0, c + c0, nullptr,
+                                       false, k);
+        if (rc != BOF_OK) return rc;
+      }
+      return BOF_OK;
+    }
+  }
   return host_csrmm_impl(ctx, trans_a, m, n, k, alpha, beta, a, ia, ja, ord_b, b, c, nullptr);
 }
 

@@ -294,3 +294,30 @@ def test_spmv_transposed_is_deterministic_and_atomic_free_by_default(bof, ctx):
         c3.host_csrgemv("T", m, n, a, ia, ja, x, y1)
         c3.host_csrgemv("T", m, n, a, ia, ja, x, y2)
         assert oracle.rel_fro(y1, ref) <= TOL and np.array_equal(y1, y2)
+
+
+def test_host_csrmm_column_panels_child_process(tmp_path):
+    """B wider than the device budget: flash::csrmm cuts B and C into column panels and re-streams A per panel
+    (the reference's column blocks, src/blas/csrmm.cpp:64-126).  BOF_CSRMM_KPANEL forces the path at test size."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        import __graft_entry__ as g, oracle
+        bof = g.load_package()
+        rng = np.random.default_rng(4)
+        m, n, k = 3000, 2500, 200
+        a, ia, ja = oracle.gen_csr(m, n, 17, seed=9)
+        B = oracle.gen_dense((n, k), seed=10); C0 = oracle.gen_dense((m, k), seed=11)
+        with bof.Context(device=0, csrmm_max_nnz=9000) as ctx:
+            for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+                C = C0.copy() if beta else np.full((m, k), np.nan, np.float32)
+                ctx.host_csrmm("N", m, n, k, alpha, beta, a, ia, ja, "R", B, C)
+                ref = oracle.csrmm("N", m, n, k, alpha, beta, a, ia, ja, "R", B, C0, acc64=True)
+                assert oracle.rel_fro(C, ref) <= 1e-5, oracle.rel_fro(C, ref)
+            assert ctx.stats().h2d_bytes > 0
+        print("ok")
+    ''' % str(Path(__file__).resolve().parent.parent))
+    import os
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BOF_CSRMM_KPANEL="64"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
