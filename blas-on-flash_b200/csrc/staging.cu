@@ -439,6 +439,10 @@ bool wants_staging(const bof_ctx* ctx, const void* host, size_t dpitch, size_t s
 // drainer thread, which enqueues it chunk by chunk through the pinned ring while the calling thread goes on;
 // *ticket then identifies the transfer and d2h_fence(ticket) must precede any use of `record_ev` (and any
 // re-recording of `wait_ev`).  sync_all() completes every transfer.
+// Ordering contract of the pageable path: the copies are enqueued on `s` LATER, from the drainer thread, so they are
+// NOT ordered against work the caller enqueues on `s` after this call returns -- the source buffer must stay
+// untouched (and `wait_ev` unre-recorded) until d2h_fence(ticket) or sync_all().  Every call site keeps to that:
+// block buffers are reused only behind their ticket's fence, one-shot downloads are followed by sync_all().
 int d2h_transfer(bof_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
                  cudaStream_t s, cudaEvent_t wait_ev, cudaEvent_t record_ev, uint64_t* ticket) {
   if (ticket) *ticket = 0;
