@@ -192,6 +192,7 @@ class KMeans:
     def __init__(self, ctx: Context, npoints, ncenters, dim, points_host, centers_host):
         self.ctx = ctx
         self.npoints, self.ncenters, self.dim = npoints, ncenters, dim
+        self._points_host = points_host   # out-of-core shards are streamed from this buffer on every step
         h = C.c_void_p()
         ctx._check(ctx.lib.bof_kmeans_open(ctx.h, npoints, ncenters, dim, ptr(points_host), ptr(centers_host),
                                            C.byref(h)))

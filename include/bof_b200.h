@@ -324,7 +324,12 @@ BOF_API int bof_csr_close(bof_csr* h);
  * an exact integer or sum, also after adding the ranks' buffers -- in a device buffer
  * whose address is returned so that the caller can NCCL-allreduce it in place (the only
  * collective on the path); bof_kmeans_update divides and refreshes the resident centers.
- * assign_out (host, int64 as FBLAS_UINT center_index, in_mem_kmeans.cpp:82-85) may be NULL. */
+ * assign_out (host, int64 as FBLAS_UINT center_index, in_mem_kmeans.cpp:82-85) may be NULL.
+ * Out-of-core shards: when the shard with its operand planes and workspaces exceeds ~70 % of the device's memory
+ * the points are NOT kept resident; every local_step then streams them from points_host in chunks through two
+ * device buffers (upload of chunk c+1 overlapped with assign + reduce of chunk c; the reference re-reads its points
+ * from flash every iteration the same way, drivers/kmeans.cpp:143-145), and points_host MUST stay valid and
+ * unchanged until bof_kmeans_close. */
 typedef struct bof_kmeans bof_kmeans;
 BOF_API int bof_kmeans_open(bof_ctx* ctx, int64_t npoints, int64_t ncenters, int64_t dim,
                     const float* points_host, const float* centers_host, bof_kmeans** out);

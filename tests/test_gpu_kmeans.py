@@ -151,3 +151,49 @@ def test_distance_tile_flash_kmeans(ctx, ord_):
     clear = margin > 1e-3                       # top-2 gap well above fp32 rounding of the distances
     assert clear.mean() > 0.9
     assert np.array_equal(np.abs(got).argmin(axis=0)[clear], a_ref[clear])
+
+
+def test_out_of_core_shard_child_process():
+    """Shards larger than HBM are streamed chunk by chunk on every iteration (the reference re-reads its points from
+    flash per iteration, drivers/kmeans.cpp:143-145).  BOF_KMEANS_CHUNK forces the mode at test size: 3 Lloyd
+    iterations with a ragged last chunk must give the resident mode's assignments and, up to the order of the
+    fp32 chunk sums, its centroids."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        import __graft_entry__ as g, oracle
+        bof = g.load_package()
+        rng = np.random.default_rng(12)
+        P, K, d = 50000, 48, 40
+        cent = (rng.normal(size=(K, d)) * 4).astype(np.float32)
+        pts = (cent[rng.integers(0, K, P)] + 0.3 * rng.normal(size=(P, d))).astype(np.float32)
+        c0 = (cent + 0.05 * rng.normal(size=(K, d))).astype(np.float32)
+        with bof.Context(device=0) as ctx:
+            km = bof.KMeans(ctx, P, K, d, pts, c0)
+            for _ in range(3):
+                km.local_step(); km.update()
+            got_c = np.zeros((K, d), np.float32); got_a = np.zeros(P, np.int64)
+            km.get(got_c, got_a); km.close()
+        ref_c = c0
+        for _ in range(3):
+            prev = ref_c
+            ref_c, ref_a, _ = oracle.lloyd_iter(pts, prev)
+        _, margin = oracle.kmeans_assign(pts, prev)
+        ok = margin > 1e-3 * (1 + np.einsum("ij,ij->i", pts, pts))
+        assert ok.mean() > 0.99
+        assert np.array_equal(got_a[ok], ref_a[ok])
+        assert oracle.rel_fro(got_c, ref_c) <= 1e-5, oracle.rel_fro(got_c, ref_c)
+        np.save(sys.argv[1], got_c)
+        print("ok")
+    ''' % str(Path(__file__).resolve().parent.parent))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for name, chunk in (("resident", "0"), ("chunked", "7000")):
+            f = os.path.join(td, name + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, BOF_KMEANS_CHUNK=chunk),
+                               capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+            outs.append(np.load(f))
+    assert oracle.rel_fro(outs[1], outs[0]) <= 2e-6
