@@ -102,9 +102,12 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   BOF_CUDA(ctx, cudaSetDevice(ctx->device));
   stats_begin(ctx);
   CallGuard call_guard(ctx);
-  if (cn.Mo == 0 || cn.No == 0) { stats_end(ctx); return call_guard.done(); }
+  // A collective call (bof_dist_gemm) must take the same decisions on every rank: N and K are common, the local M
+  // is not -- a rank whose shard is empty or tiny still owns panels of Q and takes part in the exchange.
+  const bool dist_call = dist_q && comm_world(ctx) > 1;
+  if (cn.No == 0 || (cn.Mo == 0 && !dist_call)) { stats_end(ctx); return call_guard.done(); }
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
-  const int path = pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
+  const int path = dist_call ? (ctx->cfg.gemm_force_path ? ctx->cfg.gemm_force_path : 2) : pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
   const int64_t K = cn.K, kp = padded_k(K);
   const bool tensor = (K > 0 && path != 3);
   const int cg = path == 1 ? 1 : 2;
@@ -130,6 +133,31 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   if (q_on_device) qraw = const_cast<float*>(cn.qsrc);  // B already in HBM in its source layout; read-only here
   else if (dist_mode) BOF_TRY(comm_exchange_begin(ctx, (size_t)cn.No * std::max<int64_t>(K, 1) * sizeof(float), &qraw));
   else BOF_TRY(slot_reserve(ctx, S_DENSE, (size_t)cn.No * std::max<int64_t>(K, 1), &qraw));
+  static const int64_t n_q_panels_env = getenv("BOF_GEMM_QPANELS") ? std::min(16, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 0;
+  const int64_t n_q_panels = n_q_panels_env ? n_q_panels_env : (dist_mode ? (comm_world(ctx) >= 8 ? 16 : 8) : 8);
+  if (dist_mode && cn.Mo == 0) {
+    // No rows of C on this rank: upload and push the Q panels it owns, and wait for the peers' panels so that no push
+    // into this rank's exchange buffer is still in flight when the call returns.
+    const int world = comm_world(ctx), rank = comm_rank(ctx);
+    const int64_t rows_per = std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, n_q_panels), 256));
+    const int npan = (int)ceil_div<int64_t>(cn.No, rows_per);
+    constexpr int EV_OWN = 40;
+    for (int j = 0; j < npan; ++j) {
+      const int64_t n0 = (int64_t)j * rows_per, n1 = std::min(cn.No, n0 + rows_per);
+      if (j % world == rank) {
+        int64_t sr, sk;
+        BOF_TRY(upload_rows(cn.qsrc, cn.q_sr, cn.q_sk, n0, n1, qraw + n0 * K, &sr, &sk, ctx->h2d));
+        BOF_CUDA(ctx, cudaEventRecord(get_event(ctx, EV_OWN + j), ctx->h2d));
+        BOF_TRY(comm_push(ctx, (size_t)(n0 * K), (size_t)(n1 - n0) * K, j, get_event(ctx, EV_OWN + j)));
+      } else {
+        BOF_TRY(comm_wait_item(ctx, ctx->compute, j));
+      }
+    }
+    BOF_TRY(sync_all(ctx));
+    stats_end(ctx);
+    return call_guard.done();
+  }
+  if (cn.Mo == 0) { stats_end(ctx); return call_guard.done(); }   // collective call without an exchange (K == 0 or CUDA-core path)
   const size_t qb = plane_bytes(cn.No, kp);
   if (tensor) {
     void* p;
@@ -271,8 +299,6 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   const int world = dist_q ? comm_world(ctx) : 1, rank = comm_rank(ctx);
   const bool dist = dist_mode;
   const bool q_panels = tensor && !q_on_device && (dist || (size_t)cn.No * K * 4 >= (256u << 20));
-  static const int64_t n_q_panels_env = getenv("BOF_GEMM_QPANELS") ? std::min(16, std::max(1, atoi(getenv("BOF_GEMM_QPANELS")))) : 0;
-  const int64_t n_q_panels = n_q_panels_env ? n_q_panels_env : (dist ? (world >= 8 ? 16 : 8) : 8);
   const int64_t qpan_rows = q_panels ? std::max<int64_t>(256, round_up<int64_t>(ceil_div<int64_t>(cn.No, n_q_panels), 256)) : cn.No;
   const int n_qpan = (int)ceil_div<int64_t>(cn.No, qpan_rows);
   constexpr int EV_SLAB = 88;

@@ -45,13 +45,14 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
   trace_mark(ctx, ctx->h2d, "start", 0);
   const int64_t out_rows = trans_a == 'N' ? m : n;   // rows of C
   const int64_t in_rows = trans_a == 'N' ? n : m;    // rows of B
-  if (out_rows == 0 || k == 0) { stats_end(ctx); return call_guard.done(); }
+  // a collective call (bof_dist_csrmm) exchanges the dense operand on every rank, also on one that owns no rows of C
+  const bool dist_mode = dist_b && comm_world(ctx) > 1;
+  if (k == 0 || (out_rows == 0 && !dist_mode)) { stats_end(ctx); return call_guard.done(); }
   const bool colmaj = ord_b == 'C';
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
 
   // resident dense operand, always row-major [in_rows x k] on the device
   float* Bd = nullptr;
-  const bool dist_mode = dist_b && comm_world(ctx) > 1;
   if (b_dev != nullptr) {
     Bd = const_cast<float*>(b_dev);  // already in HBM (e.g. all-gathered over NVLink); read-only here
   } else if (dist_mode) {
@@ -115,6 +116,11 @@ static int host_csrmm_impl(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int
     BOF_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, evB, 0));
   }
 
+  if (out_rows == 0) {   // collective call, empty shard: my slice has been pushed and the peers' slices have arrived
+    BOF_TRY(sync_all(ctx));
+    stats_end(ctx);
+    return call_guard.done();
+  }
   trace_mark(ctx, ctx->h2d, "h2d: dense operand landed", 0);
   const int64_t* offs_host = ia;
   const int64_t nnz = ia[m] - ia[0];

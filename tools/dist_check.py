@@ -59,6 +59,18 @@ def main():
     out["gemm_big_sampled"] = float(np.abs(c_loc[ii, jj] - ref).max() / np.abs(ref).max())
     assert out["gemm_big_sampled"] <= TOL and not np.isnan(c_loc).any()
 
+    # uneven shards: the last rank owns no rows of C / a single row (a tiny product) -- it still owns panels of B and
+    # must take part in the exchange
+    for last_rows in ((0, 1) if world > 1 else (1,)):
+        M, N, K = 600 * (world - 1) + last_rows, 1300, 900
+        a, b, c0 = oracle.gen_dense((M, K), seed=14), oracle.gen_dense((K, N), seed=15), oracle.gen_dense((M, N), seed=16)
+        r0, r1 = 600 * rank, (600 * (rank + 1) if rank < world - 1 else M)
+        c_loc = c0[r0:r1].copy()
+        ctx.dist_gemm("N", "N", r1 - r0, N, K, 1.5, 0.5, np.ascontiguousarray(a[r0:r1]), b, c_loc)
+        ref = oracle.gemm("R", "N", "N", M, N, K, 1.5, 0.5, a, b, c0, acc64=True)
+        assert r1 == r0 or oracle.rel_fro(c_loc, ref[r0:r1]) <= TOL, (rank, r0, r1)
+    out["gemm_uneven_rows"] = True
+
     # ---- csrmm: nnz-balanced row shards, B shared
     m, n, k = 50000, 40000, 96
     av, ia, ja = oracle.gen_csr(m, n, 24, seed=6)
@@ -70,6 +82,14 @@ def main():
     ref = oracle.csrmm("N", m, n, k, 1.25, 0.75, av, ia, ja, "R", B, C0, acc64=True)
     out["csrmm"] = oracle.rel_fro(c_loc, ref[r0:r1])
     assert out["csrmm"] <= TOL
+
+    # empty shard on the last rank (all rows on the others)
+    r0, r1 = (bdist.nnz_balanced_shard(ia, world - 1, rank) if rank < world - 1 else (m, m)) if world > 1 else (0, m)
+    z0, z1 = int(ia[r0]), int(ia[r1])
+    c_loc = C0[r0:r1].copy()
+    ctx.dist_csrmm(r1 - r0, n, k, 1.25, 0.75, av[z0:z1], ia[r0:r1 + 1], ja[z0:z1], B, c_loc)
+    assert r1 == r0 or oracle.rel_fro(c_loc, ref[r0:r1]) <= TOL
+    out["csrmm_empty_last_shard"] = True
 
     # ---- kmeans: sharded + allreduce inside the library == the oracle on the whole set (ties-free start)
     rng = np.random.default_rng(9)
