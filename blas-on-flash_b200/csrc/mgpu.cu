@@ -1,9 +1,17 @@
 // One process, several GPUs: the flash:: entry points of a C++ application (and drivers/*.cpp) spread over the
 // GPUs of the node without Python or a launcher.  A bof_mgpu owns one context + communicator rank per device;
-// every call runs one host thread per device, each driving its rank's share through the same bof_dist_* /
-// bof_host_* pipelines a torchrun rank would use (north_star (5): output row blocks sharded with no collective;
-// the replicated dense operand crosses PCIe once per node and is broadcast over NVLink; k-means allreduces
+// every call runs one host thread per device (north_star (5): output row blocks sharded with no collective; the
+// replicated dense operand crosses PCIe once per node and is copied to the peers over NVLink; k-means allreduces
 // centroid sums and counts).  Host operands are shared by all threads: one copy of B in host memory instead of N.
+//
+// Calls are organised in PHASES separated by a join of the per-device threads, and inside a phase no thread's
+// progress depends on another thread's CUDA calls.  The flag-gated exchange of bof_dist_* (streams parked on
+// cuStreamWaitValue32 until a peer's push arrives) is for one process per GPU only: inside one process, with peer
+// access enabled, a cudaMalloc / cudaHostAlloc on one device can need the other devices' work to drain, which a
+// parked stream never does -- seen as an intermittent hang at 4 GPUs (profiles/r02/t17_mgpu_check_hang.txt).
+// Here the replicated operand is therefore completed on every device first (own slice uploaded, then pushed to the
+// peers with copy-engine peer copies, everything stream-ordered on the pushing device), the threads join, and each
+// device then runs the ordinary single-GPU pipeline against its resident copy (bof_host_*_devb).
 #include "host_internal.cuh"
 
 #include <thread>
@@ -21,6 +29,8 @@ int bof_dist_csrmm(bof_ctx* ctx, int64_t m_local, int64_t n, int64_t k, float al
 
 struct bof_mgpu {
   std::vector<bof_ctx*> ctx;
+  std::vector<cudaStream_t> push;   // per device: peer copies of the replicated operand
+  std::vector<float*> rep;          // per device: the replicated dense operand of the call in flight
   std::string err;
 };
 
@@ -65,6 +75,45 @@ void split_nnz(const int64_t* ia, int64_t m, int world, int r, int64_t* r0, int6
   *r1 = std::max(*r0, std::min(cut(r + 1), m));
 }
 
+// Complete a host matrix of `rows` stored rows x `cols` floats (row pitch `ld`) on every device as a tight
+// [rows x cols] array in mg->rep[r]: phase 1 reserves the buffers, phase 2 uploads 1/world of the rows per device
+// (in pieces, so that pushes start while the rest uploads) and pushes each piece to every peer.
+int replicate_rows(bof_mgpu* mg, const float* src, int64_t rows, int64_t cols, int64_t ld) {
+  const int world = (int)mg->ctx.size();
+  const size_t count = (size_t)std::max<int64_t>(rows * cols, 1);
+  int rc = for_each_rank(mg, [&](int r) {
+    bof_ctx* ctx = mg->ctx[r];
+    BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+    return slot_reserve(ctx, S_DENSE, count, &mg->rep[r]);
+  });
+  if (rc != BOF_OK || rows == 0 || cols == 0) return rc;
+  constexpr int kPieces = 4;
+  return for_each_rank(mg, [&](int r) {
+    bof_ctx* ctx = mg->ctx[r];
+    BOF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t base = rows / world, rem = rows % world;
+    const int64_t r0 = r * base + std::min<int64_t>(r, rem), r1 = r0 + base + (r < rem ? 1 : 0);
+    const int64_t per = ceil_div<int64_t>(std::max<int64_t>(r1 - r0, 1), kPieces);
+    for (int q = 0; q < kPieces; ++q) {
+      const int64_t p0 = std::min(r1, r0 + q * per), p1 = std::min(r1, p0 + per);
+      if (p1 <= p0) continue;
+      BOF_TRY(copy2d(ctx, mg->rep[r] + p0 * cols, (size_t)cols * 4, src + p0 * ld, (size_t)ld * 4, (size_t)cols * 4,
+                     (size_t)(p1 - p0), cudaMemcpyHostToDevice, ctx->h2d));
+      cudaEvent_t ev = get_event(ctx, 100 + q);
+      BOF_CUDA(ctx, cudaEventRecord(ev, ctx->h2d));
+      BOF_CUDA(ctx, cudaStreamWaitEvent(mg->push[r], ev, 0));
+      for (int d = 1; d < world; ++d) {
+        const int peer = (r + d) % world;   // every device starts with a different peer
+        BOF_CUDA(ctx, cudaMemcpyPeerAsync(mg->rep[peer] + p0 * cols, mg->ctx[peer]->device, mg->rep[r] + p0 * cols, ctx->device,
+                                          (size_t)(p1 - p0) * cols * 4, mg->push[r]));
+      }
+    }
+    BOF_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
+    BOF_CUDA(ctx, cudaStreamSynchronize(mg->push[r]));
+    return (int)BOF_OK;
+  });
+}
+
 }  // namespace
 
 extern "C" {
@@ -88,6 +137,15 @@ int bof_mgpu_create(const bof_config* cfg, int ndev, const int* devices, bof_mgp
       return rc;
     }
     mg->ctx.push_back(x);
+    cudaStream_t st = nullptr;
+    if (cudaSetDevice(c.device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      for (bof_ctx* y : mg->ctx) bof_ctx_destroy(y);
+      delete mg;
+      return BOF_ECUDA;
+    }
+    mg->push.push_back(st);
+    mg->rep.push_back(nullptr);
   }
   if (ndev > 1) {
     char id[128];
@@ -105,7 +163,10 @@ int bof_mgpu_create(const bof_config* cfg, int ndev, const int* devices, bof_mgp
 
 int bof_mgpu_destroy(bof_mgpu* mg) {
   if (!mg) return BOF_OK;
-  for (bof_ctx* x : mg->ctx) bof_ctx_destroy(x);
+  for (size_t i = 0; i < mg->ctx.size(); ++i) {
+    if (i < mg->push.size() && mg->push[i] && cudaSetDevice(mg->ctx[i]->device) == cudaSuccess) cudaStreamDestroy(mg->push[i]);
+    bof_ctx_destroy(mg->ctx[i]);
+  }
   delete mg;
   return BOF_OK;
 }
@@ -128,11 +189,15 @@ int bof_mgpu_gemm(bof_mgpu* mg, char ord, char ta, char tb, int64_t m, int64_t n
   if (lda == 0) lda = ta == 'N' ? k : m;
   if (ldb == 0) ldb = tb == 'N' ? n : k;
   if (ldc == 0) ldc = n;
+  // B as stored: k x n ('N') or n x k ('T'); every device gets a tight copy
+  const int64_t b_rows = tb == 'N' ? k : n, b_cols = tb == 'N' ? n : k;
+  if (int rc = replicate_rows(mg, b, b_rows, b_cols, ldb)) return rc;
   return for_each_rank(mg, [&](int r) {
     int64_t r0, r1;
     split_rows(m, world, r, 256, &r0, &r1);
+    if (r1 == r0) return (int)BOF_OK;
     const float* a_loc = ta == 'N' ? a + r0 * lda : a + r0;   // 'T': a column range of the stored k x m matrix
-    return bof_dist_gemm(mg->ctx[r], ta, tb, r1 - r0, n, k, alpha, beta, a_loc, b, c + r0 * ldc, lda, ldb, ldc);
+    return bof_host_gemm_devb(mg->ctx[r], ta, tb, r1 - r0, n, k, alpha, beta, a_loc, mg->rep[r], c + r0 * ldc, lda, b_cols, ldc);
   });
 }
 
@@ -143,11 +208,13 @@ int bof_mgpu_csrmm(bof_mgpu* mg, char trans_a, int64_t m, int64_t n, int64_t k, 
   const int world = (int)mg->ctx.size();
   if (world == 1 || trans_a != 'N' || ord_b != 'R' || m < world)
     return bof_host_csrmm(mg->ctx[0], trans_a, m, n, k, alpha, beta, a, ia, ja, ord_b, b, c);
+  if (int rc = replicate_rows(mg, b, n, k, k)) return rc;
   return for_each_rank(mg, [&](int r) {
     int64_t r0, r1;
     split_nnz(ia, m, world, r, &r0, &r1);
+    if (r1 == r0) return (int)BOF_OK;
     const int64_t z0 = ia[r0] - ia[0];
-    return bof_dist_csrmm(mg->ctx[r], r1 - r0, n, k, alpha, beta, a + z0, ia + r0, ja + z0, b, c + r0 * k);
+    return bof_host_csrmm_devb(mg->ctx[r], r1 - r0, n, k, alpha, beta, a + z0, ia + r0, ja + z0, mg->rep[r], c + r0 * k);
   });
 }
 
@@ -185,16 +252,28 @@ int bof_mgpu_kmeans_lloyd(bof_mgpu* mg, int64_t npoints, int64_t ncenters, int64
   const int world = (int)mg->ctx.size();
   std::vector<float> c0((size_t)ncenters * dim);
   memcpy(c0.data(), centers_host, c0.size() * 4);   // every rank starts from the same centres; rank 0 writes the result
-  return for_each_rank(mg, [&](int r) {
+  // phases (see the top of the file): every shard opened (allocations) before the first NCCL kernel is enqueued,
+  // every rank's iterations finished before anything is freed
+  std::vector<bof_kmeans*> km((size_t)world, nullptr);
+  int rc = for_each_rank(mg, [&](int r) {
     int64_t p0, p1;
     split_rows(npoints, world, r, 1, &p0, &p1);
-    bof_kmeans* km = nullptr;
-    int rc = bof_kmeans_open(mg->ctx[r], p1 - p0, ncenters, dim, points_host + p0 * dim, c0.data(), &km);
-    if (rc == BOF_OK) rc = bof_kmeans_lloyd(km, iters);
-    if (rc == BOF_OK) rc = bof_kmeans_get(km, r == 0 ? centers_host : nullptr, assign_out ? assign_out + p0 : nullptr);
-    if (km) bof_kmeans_close(km);
-    return rc;
+    int rc1 = bof_kmeans_open(mg->ctx[r], p1 - p0, ncenters, dim, points_host + p0 * dim, c0.data(), &km[r]);
+    if (rc1 == BOF_OK) rc1 = bof_kmeans_local_step(km[r], nullptr, nullptr);   // warm-up: workspaces and kernels in place
+    if (rc1 == BOF_OK && cudaStreamSynchronize(as_stream(bof_kmeans_stream(km[r]))) != cudaSuccess) rc1 = BOF_ECUDA;
+    return rc1;
   });
+  if (rc == BOF_OK) rc = for_each_rank(mg, [&](int r) {
+    int64_t p0, p1;
+    split_rows(npoints, world, r, 1, &p0, &p1);
+    int rc1 = bof_kmeans_lloyd(km[r], iters);
+    if (rc1 == BOF_OK) rc1 = bof_kmeans_get(km[r], r == 0 ? centers_host : nullptr, assign_out ? assign_out + p0 : nullptr);
+    return rc1;
+  });
+  const std::string first_err = mg->err;
+  for_each_rank(mg, [&](int r) { if (km[r]) bof_kmeans_close(km[r]); return (int)BOF_OK; });
+  if (rc != BOF_OK) mg->err = first_err;
+  return rc;
 }
 
 }  // extern "C"
