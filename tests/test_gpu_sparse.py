@@ -183,13 +183,14 @@ def test_spmm_kernel_variants_child_process(variant):
 
 def test_failed_call_leaves_the_context_usable(bof, ctx):
     """An entry point that fails part-way (device allocation of a 400 GB operand) returns an error, leaves nothing
-    running, and the next call on the same context is correct."""
+    running, and the next call on the same context is correct.  Column-major B: a row-major B of that size is a
+    legitimate input since round 2 (processed in column panels) and would be read from the host."""
     rng = np.random.default_rng(21)
     m, n, k = 600, 500, 32
     a, ia, ja = ragged_csr(rng, m, n, 20)
     B = rng.random((n, k), dtype=np.float32); C = np.zeros((m, k), np.float32)
     with pytest.raises(bof.BofError):
-        ctx.host_csrmm("N", m, 1 << 30, 100, 1.0, 0.0, a, ia, ja, "R", B, C)   # B would be 2^30 x 100 floats
+        ctx.host_csrmm("N", m, 1 << 30, 100, 1.0, 0.0, a, ia, ja, "C", B, C)   # B would be 2^30 x 100 floats
     assert "failed" in ctx.last_error().lower() or "memory" in ctx.last_error().lower()
     ctx.host_csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, C)
     assert oracle.rel_fro(C, oracle.csrmm("N", m, n, k, 1.0, 0.0, a, ia, ja, "R", B, np.zeros((m, k), np.float32), acc64=True)) <= TOL

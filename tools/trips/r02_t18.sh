@@ -4,7 +4,11 @@
 set -u
 cd "$(dirname "$0")/../.."
 OUT=gpurun_out/r02_t18; mkdir -p $OUT
+STEP=${1:-all}
+if [ "$STEP" = tests ] || [ "$STEP" = all ]; then
 timeout 170 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -30 > $OUT/tests.txt; tail -6 $OUT/tests.txt
+fi
+if [ "$STEP" = tests ]; then exit 0; fi
 timeout 100 python bench.py --extra pcie,cfg1,cfg4,cfg5 > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err; echo "bench rc=$?"
 python - <<'PY'
 import json
