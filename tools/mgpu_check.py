@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One process driving several GPUs (bof_mgpu_*, what BOF_GPUS=n enables behind flash::): gemm in every layout incl.
 shards without rows, csrmm, csrgemv N/T, k-means with the in-library allreduce -- each against the oracle.
-Run by tests/test_gpu_multi.py in a child process so that a hang is a test failure, not a stalled suite."""
+Run by tests/test_gpu_zz_multi.py in a child process so that a hang is a test failure, not a stalled suite."""
 import sys
 from pathlib import Path
 
