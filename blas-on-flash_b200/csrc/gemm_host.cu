@@ -106,7 +106,7 @@ static int host_gemm_impl(bof_ctx* ctx, char ord, char ta, char tb, int64_t m, i
   // is not -- a rank whose shard is empty or tiny still owns panels of Q and takes part in the exchange.
   const bool dist_call = dist_q && comm_world(ctx) > 1;
   if (cn.No == 0 || (cn.Mo == 0 && !dist_call)) { stats_end(ctx); return call_guard.done(); }
-  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
   const int path = dist_call ? (ctx->cfg.gemm_force_path ? ctx->cfg.gemm_force_path : 2) : pick_gemm_path(ctx, cn.Mo, cn.No, cn.K);
   const int64_t K = cn.K, kp = padded_k(K);
   const bool tensor = (K > 0 && path != 3);

@@ -562,7 +562,7 @@ int bof_csr_mm(bof_csr* h, char trans_a, int64_t k, float alpha, float beta, cha
   const int64_t out_rows = t ? h->n : h->m, in_rows = t ? h->m : h->n;
   if (out_rows == 0 || k == 0) { stats_end(ctx); return call_guard.done(); }
   const bool colmaj = ord_b == 'C';
-  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
   const float* vals = h->vals[t];
   const int32_t* idx = h->idx[t];
   const int64_t* offs = h->offs[t];

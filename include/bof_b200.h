@@ -7,10 +7,10 @@
  *
  *   1. context / diagnostics
  *   2. device-tile kernels: operands already in HBM; `stream` is a cudaStream_t passed as void*
- *      (replace the per-tile `BaseTask::execute()` bodies, include/tasks/*.h, i.e. the MKL calls)
+ *      (replace the per-tile `BaseTask::execute()` bodies, include/tasks/<task>.h, i.e. the MKL calls)
  *   3. host entry points: operands in host memory (pageable, pinned or a file mmap, i.e. the
  *      `flash_ptr<T>::ptr` of include/pointers/pointer.h:15-27); the library streams them through
- *      pinned staging buffers and CUDA streams (replace src/scheduler/* + src/file_handles/* for
+ *      pinned staging buffers and CUDA streams (replace src/scheduler/ + src/file_handles/ for
  *      this path) and the result is in the host buffer when the call returns
  *      (reference contract: Scheduler::flush_cache() at kernel end, src/blas/gemm.cpp:200).
  *
