@@ -288,11 +288,17 @@ int bof_host_csrmm(bof_ctx* ctx, char trans_a, int64_t m, int64_t n, int64_t k, 
     cudaSetDevice(ctx->device);
     const int64_t kp = csrmm_column_panel(ctx, n, k);
     if (kp > 0) {   // B does not fit in HBM: one pass over A per column panel of B and C
+      bof_stats sum{};
       for (int64_t c0 = 0; c0 < k; c0 += kp) {
         const int rc = host_csrmm_impl(ctx, 'N', m, n, std::min(kp, k - c0), alpha, beta, a, ia, ja, 'R', b + c0, c + c0, nullptr,
                                        false, k);
         if (rc != BOF_OK) return rc;
+        const bof_stats& st = ctx->stats;   // bof_get_stats reports the whole call, not the last panel
+        sum.h2d_bytes += st.h2d_bytes; sum.d2h_bytes += st.d2h_bytes; sum.stage_in_ms += st.stage_in_ms;
+        sum.stage_out_ms += st.stage_out_ms; sum.total_ms += st.total_ms; sum.kernel_launches += st.kernel_launches;
+        sum.kernel_ms = st.kernel_ms;
       }
+      ctx->stats = sum;
       return BOF_OK;
     }
   }
