@@ -21,6 +21,38 @@ NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
 need2 = pytest.mark.skipif(NGPU < 2, reason="needs at least 2 GPUs")
 
 
+class _Done:
+    def __init__(self, returncode, stdout, stderr):
+        self.returncode, self.stdout, self.stderr = returncode, stdout, stderr
+
+
+def run_bounded(cmd, timeout, env=None):
+    """subprocess.run with a deadline that ends the WHOLE process tree, so that workers blocked in a collective
+    cannot outlive the test and keep the GPUs busy for whatever runs next.  The child gets its own session; on a
+    time-out its group first gets SIGTERM -- torchrun starts every worker in a session of its own and only its
+    SIGTERM handler reaches them (elastic SubprocessHandler.close -> killpg per worker) -- then SIGKILL."""
+    import signal
+    p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        for sig, grace in ((signal.SIGTERM, 45), (signal.SIGKILL, 10)):
+            try:
+                os.killpg(p.pid, sig)   # pid == pgid == sid of the child
+            except ProcessLookupError:
+                pass
+            try:
+                out, err = p.communicate(timeout=grace)
+                break
+            except subprocess.TimeoutExpired:
+                continue
+        else:
+            out, err = "", ""
+        return _Done(-9, out, (err or "") + "\n[run_bounded] ended the process tree after %d s" % timeout)
+    return _Done(p.returncode, out, err)
+
+
+
 def test_dist_entry_points_at_world_one(bof, ctx):
     """without a communicator bof_dist_* are the plain pipelines and bof_kmeans_allreduce is a no-op"""
     assert ctx.comm_world() == 1
@@ -67,7 +99,7 @@ def test_kmeans_count_split_is_exact(bof, ctx):
 def test_mgpu_one_process():
     """tools/mgpu_check.py in a child process with a deadline: a missed hand-shake between the per-GPU threads shows up
     as a failure here instead of stalling the whole suite"""
-    r = subprocess.run([sys.executable, str(ROOT / "tools" / "mgpu_check.py")], capture_output=True, text=True, timeout=240)
+    r = run_bounded([sys.executable, str(ROOT / "tools" / "mgpu_check.py")], 240)
     assert r.returncode == 0 and "mgpu ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
@@ -75,8 +107,8 @@ def test_mgpu_one_process():
 def test_dist_paths_under_torchrun():
     n = min(NGPU, 4)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", str(ROOT / "tools" / "dist_check.py")], env=env, capture_output=True, text=True, timeout=240)
+    r = run_bounded([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(ROOT / "tools" / "dist_check.py")], 240, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"comm_world": %d' % n in r.stdout
 
@@ -93,8 +125,8 @@ def test_cpp_drivers_with_bof_gpus(tmp_path):
     M, N, K = 3000, 2200, 1600
     A = rng.random((M, K), dtype=np.float32); B = rng.random((K, N), dtype=np.float32); C0 = rng.random((M, N), dtype=np.float32)
     A.tofile(tmp_path / "A.bin"); B.tofile(tmp_path / "B.bin"); C0.tofile(tmp_path / "C.bin")
-    r = subprocess.run([str(binp / "gemm"), *map(str, (tmp_path / "A.bin", tmp_path / "B.bin", tmp_path / "C.bin", M, K, N, 1.0, 0.5,
-                                                      "N", "N", "R", 0, 0, 0))], env=env, capture_output=True, text=True, timeout=240)
+    r = run_bounded([str(binp / "gemm"), *map(str, (tmp_path / "A.bin", tmp_path / "B.bin", tmp_path / "C.bin", M, K, N, 1.0, 0.5,
+                                                   "N", "N", "R", 0, 0, 0))], 240, env=env)
     assert r.returncode == 0 and "returned 0" in r.stdout, r.stdout + r.stderr
     got = np.fromfile(tmp_path / "C.bin", dtype=np.float32).reshape(M, N)
     assert oracle.rel_fro(got, oracle.gemm("R", "N", "N", M, N, K, 1.0, 0.5, A, B, C0, acc64=True)) <= TOL
@@ -103,9 +135,8 @@ def test_cpp_drivers_with_bof_gpus(tmp_path):
     Bd = oracle.gen_dense((n, k), seed=6); Cd = oracle.gen_dense((m, k), seed=7)
     av.tofile(tmp_path / "A.csr"); ja.tofile(tmp_path / "A.col"); ia.tofile(tmp_path / "A.off")
     Bd.tofile(tmp_path / "B2.bin"); Cd.tofile(tmp_path / "C2.bin")
-    r = subprocess.run([str(binp / "csrmm"), *map(str, (tmp_path / "A.csr", tmp_path / "A.col", tmp_path / "A.off", tmp_path / "B2.bin",
-                                                       tmp_path / "C2.bin", m, n, k, 1.0, 0.5, "N", "R"))], env=env, capture_output=True,
-                       text=True, timeout=240)
+    r = run_bounded([str(binp / "csrmm"), *map(str, (tmp_path / "A.csr", tmp_path / "A.col", tmp_path / "A.off", tmp_path / "B2.bin",
+                                                    tmp_path / "C2.bin", m, n, k, 1.0, 0.5, "N", "R"))], 240, env=env)
     assert r.returncode == 0 and "returned 0" in r.stdout, r.stdout + r.stderr
     got = np.fromfile(tmp_path / "C2.bin", dtype=np.float32).reshape(m, k)
     assert oracle.rel_fro(got, oracle.csrmm("N", m, n, k, 1.0, 0.5, av, ia, ja, "R", Bd, Cd, acc64=True)) <= TOL
